@@ -90,14 +90,19 @@ def test_slm_exhaustive():
 def test_code_tables_and_decoder():
     assert np.array_equal(rb.pr3(), ob.sync_vector())
     rng = np.random.default_rng(9)
-    for _ in range(20):
-        soft = rng.integers(0, 256, 162).astype(np.uint8)
+    for trial in range(20):
+        if trial % 2:
+            soft = rng.integers(0, 256, 162).astype(np.uint8)  # times out
+        else:  # a decodable word with a few corrupted symbols
+            data = np.zeros(11, np.uint8)
+            data[:7] = td.message_bytes(rng)
+            soft = np.where(ob.encode(data)[:162] == 1, 190, 66).astype(np.uint8)
+            soft[rng.integers(0, 162, 12)] = 128
         r = rb.fano_decode(soft, maxcycles=200)
         o = ob.fano(soft, maxcycles=200)
         assert r[0] == o[0] and r[2:] == o[2:]
-        # decoded bytes come from nodes 7+8b; nodes past maxnp+1 are uninitialised heap in the reference
-        nb = max(0, (r[4] + 1 - 7) // 8 + 1) if r[4] + 1 >= 7 else 0
-        assert np.array_equal(r[1][:min(nb, 10)], o[1][:min(nb, 10)])
+        if r[0] == 0:  # on a time-out the reference returns uninitialised heap for unvisited nodes
+            assert np.array_equal(r[1][:10], o[1][:10])
 
 
 def test_sliding_window_against_reference_block():
