@@ -1,0 +1,612 @@
+// C ABI of libuwspr_b200.so (include/uwspr_b200.h): context, constant tables, chunked
+// submission with copy/compute overlap.  No CPU fallback exists for the ported stages:
+// without a usable CUDA device uwspr_b200_create fails.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "../host/wspr_tables.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace {
+
+const int kMaxChunks = 1024;
+
+struct Buffers {
+    // per chunk
+    float2 *x_stage[2] = { nullptr, nullptr };  // host-fed samples, double buffered
+    size_t x_stage_elems = 0;
+    float *amp = nullptr;
+    float *ps_dbg = nullptr;
+    float *psavg = nullptr;
+    UwPeak *peaks = nullptr;
+    // per call
+    int *npk = nullptr;
+    int *base = nullptr;
+    size_t win_cap = 0;
+    UwItem *items = nullptr;
+    uwspr_b200_candidate_t *cands = nullptr;
+    uwspr_b200_refined_t *refined = nullptr;
+    uwspr_b200_jiggle_t *jig = nullptr;
+    uint8_t *soft = nullptr;
+    int *counters = nullptr;  // [0] running total, [1] overflow, [2] ticket coarse, [3] ticket fine, [4] chunk lo
+    // tables
+    float *window = nullptr;
+    float2 *twiddle = nullptr;
+    uint32_t *off4 = nullptr;
+    short *hyp_unique = nullptr;
+};
+
+}  // namespace
+
+struct uwspr_b200_ctx {
+    uwspr_b200_params_t prm;
+    UwDims d;
+    Buffers b;
+    int device = 0, sm_count = 0;
+    int chunk_windows = 0, max_windows = 0, max_candidates = 0;
+    int grid_coarse = 0, grid_fine = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    bool own_compute = true;
+    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };
+    std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    float ms[4] = { 0, 0, 0, 0 };
+    int64_t launches = 0;
+    std::string err;
+    bool debug_ps = false;
+    bool have_coarse = false;  // device candidate list valid for a following fine call
+    int last_nwin = 0, last_total = 0;
+    const float *last_samples = nullptr;
+    int64_t last_stride = 0;
+};
+
+namespace {
+
+int fail(uwspr_b200_ctx *c, int status, const std::string &msg)
+{
+    if (c) c->err = msg;
+    return status;
+}
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(ctx, UWSPR_B200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// lib/slm.cc:36-73 restated for the host-side table build (double inside, fp32 result)
+float slm_frequency_drift_host(double V1, double V2, int p1, int p2, float cf, float t)
+{
+    const double q1 = V1 * t + p1, q2 = V2 * t + p2;
+    const float sign = (float)(((q1 * V1 + q2 * V2) > 0) * 2 - 1);
+    const double num = fabs(V1 * q1 + V2 * q2);
+    const double den = sqrt(q1 * q1 + q2 * q2);
+    if (den == 0) return 0.0f;
+    return (float)(-sign * num / den * cf / 1500.0f);
+}
+
+// Builds every table that depends only on the constructor arguments.
+int build_tables(uwspr_b200_ctx *ctx, std::vector<uint32_t> &off4, std::vector<short> &hyp_unique)
+{
+    UwDims &d = ctx->d;
+    const uwspr_b200_params_t &p = ctx->prm;
+    d.fl = p.fl;
+    d.size = 2 * p.spb;                                           // FDR_impl.cc:81
+    d.df = (float)p.fs / (float)d.size;                           // :93
+    d.m = d.size / 2;                                             // :95
+    d.hpbm = (int)ceilf((float)(int)(float)p.halfbandwidth / d.df);  // :97
+    d.finpb = 2 * d.hpbm;                                         // :265
+    d.noiseidx = (int)floor(0.3 * (float)d.finpb);                // :283
+    d.n_rows = (int)(floor(((float)p.fl / (float)p.spb) * 2.0) - 3);  // :109
+    d.min_snr = (float)pow(10.0, -7.0 / 10.0);                    // :137
+    d.floor_val = (float)(0.1 * d.min_snr);                       // :290
+    d.threshold = (float)p.threshold;                             // :79
+    d.maxfreqs = p.maxfreqs;
+    d.maxdrift = p.maxdrift;
+    d.cf = p.cf;
+    d.nonlinear_intended_t = p.nonlinear_intended_t ? 1 : 0;
+    for (int q = 0; q < 6; q++) d.sync_words[q] = WSPR_SYNC_WORDS[q];
+    if (d.finpb < 3) return fail(ctx, UWSPR_B200_E_PARAM, "halfbandwidth too small: fewer than 3 pass-band bins");
+    d.maxcand = std::min(p.maxfreqs, (d.finpb - 1) / 2);
+    if (d.maxcand > 256) return fail(ctx, UWSPR_B200_E_PARAM, "more than 256 candidate slots per window");
+    d.n_lin = 2 * p.maxdrift + 1;
+    d.n_hyp = d.n_lin + UW_NTRAJ;
+
+    // bins the coarse search can centre on: if0 in [m-hpbm+1, m+hpbm-2], ifr = if0-2..if0+2
+    const int ifr_lo = d.m - d.hpbm - 1, ifr_hi = d.m + d.hpbm;
+    if (ifr_lo < 0) return fail(ctx, UWSPR_B200_E_PARAM, "halfbandwidth reaches past the spectrum (reference reads out of bounds)");
+    std::vector<std::vector<signed char>> seqs;
+    hyp_unique.assign(d.n_hyp, 0);
+    int off_min = 0, off_max = 0;
+    for (int h = 0; h < d.n_hyp; h++) {
+        std::vector<signed char> seq(UW_NSYM);
+        for (int k = 0; k < UW_NSYM; k++) {
+            int off_ref = 0;
+            for (int ifr = ifr_lo; ifr <= ifr_hi; ifr++) {
+                int ifd;
+                if (h < d.n_lin) {
+                    const int drift = h - p.maxdrift;
+                    // FDR_impl.cc:353 (double expression, truncated)
+                    ifd = (int)(ifr + ((float)k - 81.0) / 81.0 * ((float)drift) / (2.0 * d.df));
+                } else {
+                    const int t_idx = h - d.n_lin;  // slm.cc:76-116 order: p2 fastest, V1, V2
+                    const double V1 = (double)((t_idx / 5) % 5) - 2.0, V2 = (double)(t_idx / 25) - 2.0;
+                    const int p2 = (t_idx % 5) * 200 + 50;
+                    const float t = (float)(k * 111 / 162);                       // :382
+                    const float drift = slm_frequency_drift_host(V1, V2, 0, p2, (float)p.cf, t);
+                    ifd = (int)(ifr + drift / d.df);                              // :384-385, fp32
+                }
+                const int off = ifd - ifr;
+                if (ifr == ifr_lo)
+                    off_ref = off;
+                else if (off != off_ref)
+                    return fail(ctx, UWSPR_B200_E_PARAM, "bin offsets depend on the bin (parameters outside the supported domain)");
+            }
+            if (off_ref < -100 || off_ref > 100) return fail(ctx, UWSPR_B200_E_PARAM, "drift hypotheses span too many bins");
+            seq[k] = (signed char)off_ref;
+            off_min = std::min(off_min, off_ref);
+            off_max = std::max(off_max, off_ref);
+        }
+        int u = -1;
+        for (size_t q = 0; q < seqs.size(); q++)
+            if (seqs[q] == seq) {
+                u = (int)q;
+                break;
+            }
+        if (u < 0) {
+            u = (int)seqs.size();
+            seqs.push_back(seq);
+        }
+        hyp_unique[h] = (short)u;
+    }
+    d.n_unique = (int)seqs.size();
+    d.off_min = off_min;
+    d.off_max = off_max;
+    d.tile_w = 11 + off_max - off_min;
+    if (d.tile_w > UW_MAX_TILE_W || d.n_unique > UW_MAX_UNIQUE)
+        return fail(ctx, UWSPR_B200_E_PARAM, "drift hypotheses span too many bins / sequences for one tile");
+    // kept bins: everything the normalizer (:268-274) and powersum (:199-205) can index
+    const int lo = std::min(d.m - d.hpbm - 3, (d.m - d.hpbm + 1) - 5 + off_min);
+    const int hi = std::max(d.m + d.hpbm + 2, (d.m + d.hpbm - 2) + 5 + off_max);
+    if (lo < 0 || hi > d.size - 1)
+        return fail(ctx, UWSPR_B200_E_PARAM, "halfbandwidth too large: the reference would index outside the spectrum");
+    d.bin_lo = lo;
+    d.n_bins = hi - lo + 1;
+    d.nbp = (d.n_bins + 3) & ~3;
+    off4.assign((size_t)UW_NQUAD * d.n_unique, 0);
+    for (int u = 0; u < d.n_unique; u++)
+        for (int k = 0; k < UW_NSYM; k++)
+            off4[(size_t)(k / 4) * d.n_unique + u] |= (uint32_t)(seqs[u][k] - off_min) << (8 * (k % 4));
+    return UWSPR_B200_OK;
+}
+
+int ensure_window_capacity(uwspr_b200_ctx *ctx, int nwin)
+{
+    Buffers &b = ctx->b;
+    if ((size_t)nwin + 1 <= b.win_cap) return UWSPR_B200_OK;
+    if (b.npk) cudaFree(b.npk);
+    if (b.base) cudaFree(b.base);
+    b.npk = nullptr;
+    b.base = nullptr;
+    const size_t n = (size_t)nwin + 1;
+    CU(cudaMalloc(&b.npk, n * sizeof(int)));
+    CU(cudaMalloc(&b.base, n * sizeof(int)));
+    b.win_cap = n;
+    return UWSPR_B200_OK;
+}
+
+int ensure_stage(uwspr_b200_ctx *ctx, size_t elems)
+{
+    Buffers &b = ctx->b;
+    if (elems <= b.x_stage_elems) return UWSPR_B200_OK;
+    for (int q = 0; q < 2; q++) {
+        if (b.x_stage[q]) cudaFree(b.x_stage[q]);
+        b.x_stage[q] = nullptr;
+    }
+    b.x_stage_elems = 0;
+    for (int q = 0; q < 2; q++) CU(cudaMalloc(&b.x_stage[q], elems * sizeof(float2)));
+    b.x_stage_elems = elems;
+    return UWSPR_B200_OK;
+}
+
+// The core: runs the requested stages over nwin windows in chunks.
+//   do_coarse: spectrogram + normalizer + peaks + coarse search -> device candidate list
+//   do_fine:   refinement + soft symbols for the device candidate list
+// When !do_coarse the candidate list (npk + cands) is uploaded from the caller first.
+int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin, bool do_coarse,
+        bool do_fine, const int32_t *npk_in, const uwspr_b200_candidate_t *cands_in, int total_in, int jig_first,
+        int jig_count, int32_t *npk_out, uwspr_b200_candidate_t *cands_out, int cap_out, int32_t *total_out,
+        uwspr_b200_refined_t *refined_out, uwspr_b200_jiggle_t *jig_out, uint8_t *soft_out)
+{
+    if (!ctx) return UWSPR_B200_E_PARAM;
+    if (nwin < 0 || !samples || win_stride < 0) return fail(ctx, UWSPR_B200_E_PARAM, "bad sample arguments");
+    if (nwin > ctx->max_windows) return fail(ctx, UWSPR_B200_E_PARAM, "nwin exceeds max_windows of the context");
+    if (do_fine && (jig_first < 0 || jig_count < 0 || jig_first + jig_count > UWSPR_B200_NJIG))
+        return fail(ctx, UWSPR_B200_E_PARAM, "jiggle range outside [0,17)");
+    CU(cudaSetDevice(ctx->device));
+    Buffers &b = ctx->b;
+    const UwDims &d = ctx->d;
+    cudaStream_t cs = ctx->compute;
+    int rc = ensure_window_capacity(ctx, nwin);
+    if (rc) return rc;
+    for (int q = 0; q < 4; q++) ctx->ms[q] = 0.0f;
+    if (nwin == 0) {
+        if (total_out) *total_out = 0;
+        ctx->last_total = 0;
+        ctx->last_nwin = 0;
+        return UWSPR_B200_OK;
+    }
+    const int cw = ctx->chunk_windows;
+    const int nchunks = (nwin + cw - 1) / cw;
+    if (nchunks > kMaxChunks) return fail(ctx, UWSPR_B200_E_PARAM, "too many chunks: raise max_windows");
+    while ((int)ctx->ev.size() < 4 * nchunks) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ctx->ev.push_back(e);
+    }
+    CU(cudaEventRecord(ctx->ev_begin, cs));
+    CU(cudaMemsetAsync(b.counters, 0, 8 * sizeof(int), cs));
+    if (!do_coarse) {
+        // candidate list comes from the caller (or stays from the previous coarse call)
+        if (cands_in) {
+            if (!npk_in) return fail(ctx, UWSPR_B200_E_PARAM, "cands given without npk");
+            if (total_in > ctx->max_candidates) return fail(ctx, UWSPR_B200_E_CAPACITY, "more candidates than max_candidates");
+            CU(cudaMemcpyAsync(b.npk, npk_in, sizeof(int) * nwin, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(b.cands, cands_in, sizeof(uwspr_b200_candidate_t) * (size_t)total_in,
+                               cudaMemcpyHostToDevice, cs));
+        } else if (!ctx->have_coarse || ctx->last_nwin != nwin) {
+            return fail(ctx, UWSPR_B200_E_STATE, "no candidate list on the device for these windows");
+        }
+    }
+    const size_t span_max = (size_t)(cw - 1) * (size_t)win_stride + (size_t)d.fl;
+    if (space == UWSPR_B200_HOST) {
+        rc = ensure_stage(ctx, span_max);
+        if (rc) return rc;
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int w0 = c * cw, nw = std::min(cw, nwin - w0);
+        const float2 *xdev;
+        if (space == UWSPR_B200_HOST) {
+            // copy stream: wait until the compute of chunk c-2 released this buffer, then copy
+            const int s = c & 1;
+            if (c >= 2) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
+            const size_t span = (size_t)(nw - 1) * (size_t)win_stride + (size_t)d.fl;
+            CU(cudaMemcpyAsync(b.x_stage[s], samples + 2 * (size_t)w0 * (size_t)win_stride, span * sizeof(float2),
+                               cudaMemcpyHostToDevice, ctx->copy));
+            CU(cudaEventRecord(ctx->ev_h2d[s], ctx->copy));
+            CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
+            xdev = b.x_stage[s];
+        } else {
+            xdev = reinterpret_cast<const float2 *>(samples) + (size_t)w0 * (size_t)win_stride;
+        }
+        cudaEvent_t *e = &ctx->ev[4 * c];
+        CU(cudaEventRecord(e[0], cs));
+        if (do_coarse) {
+            uw_launch_spectrogram(d, xdev, (long long)win_stride, nw, b.window, b.twiddle, b.amp,
+                                  ctx->debug_ps ? b.ps_dbg : nullptr, b.psavg, b.peaks, b.npk + w0, cs);
+            ctx->launches++;
+        }
+        CU(cudaEventRecord(e[1], cs));
+        // work list of this chunk: items [counters[4], counters[0])
+        uw_launch_worklist(b.npk + w0, nw, ctx->max_candidates, b.base + w0, b.items, b.counters, cs);
+        ctx->launches++;
+        if (do_coarse) {
+            uw_launch_coarse(d, b.amp, b.peaks, b.items, b.counters, ctx->max_candidates, b.off4, b.hyp_unique,
+                             b.cands, b.counters + 2, ctx->grid_coarse, cs);
+            ctx->launches++;
+        }
+        CU(cudaEventRecord(e[2], cs));
+        if (do_fine) {
+            uw_launch_fine(d, xdev, (long long)win_stride, b.items, b.counters, ctx->max_candidates, b.cands, jig_first,
+                           jig_count, b.refined, b.jig, b.soft, b.counters + 3, ctx->grid_fine, cs);
+            ctx->launches++;
+        }
+        CU(cudaEventRecord(e[3], cs));
+        if (space == UWSPR_B200_HOST) CU(cudaEventRecord(ctx->ev_free[c & 1], cs));
+    }
+    int h_counters[8];
+    CU(cudaMemcpyAsync(h_counters, b.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
+    CU(cudaGetLastError());
+    const int total = h_counters[0];
+    if (h_counters[1]) return fail(ctx, UWSPR_B200_E_CAPACITY, "more candidates than max_candidates of the context");
+    if (total_out) *total_out = total;
+    if (do_coarse) {
+        if (cands_out && total > cap_out) return fail(ctx, UWSPR_B200_E_CAPACITY, "more candidates than the caller's cap");
+    } else if (cands_in && total != total_in) {
+        return fail(ctx, UWSPR_B200_E_PARAM, "sum of npk differs from total");
+    }
+    if (npk_out) CU(cudaMemcpyAsync(npk_out, b.npk, sizeof(int) * nwin, cudaMemcpyDeviceToHost, cs));
+    if (cands_out && total)
+        CU(cudaMemcpyAsync(cands_out, b.cands, sizeof(uwspr_b200_candidate_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+    if (do_fine && total) {
+        if (refined_out)
+            CU(cudaMemcpyAsync(refined_out, b.refined, sizeof(uwspr_b200_refined_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+        if (jig_out)
+            CU(cudaMemcpyAsync(jig_out, b.jig, sizeof(uwspr_b200_jiggle_t) * (size_t)total * jig_count, cudaMemcpyDeviceToHost, cs));
+        if (soft_out)
+            CU(cudaMemcpyAsync(soft_out, b.soft, (size_t)total * jig_count * UW_NSYM, cudaMemcpyDeviceToHost, cs));
+    }
+    CU(cudaEventRecord(ctx->ev_end, cs));
+    CU(cudaStreamSynchronize(cs));
+    for (int c = 0; c < nchunks; c++) {
+        float t;
+        for (int q = 0; q < 3; q++) {
+            CU(cudaEventElapsedTime(&t, ctx->ev[4 * c + q], ctx->ev[4 * c + q + 1]));
+            ctx->ms[q] += t;
+        }
+    }
+    CU(cudaEventElapsedTime(&ctx->ms[3], ctx->ev_begin, ctx->ev_end));
+    ctx->have_coarse = true;
+    ctx->last_nwin = nwin;
+    ctx->last_total = total;
+    ctx->last_samples = samples;
+    ctx->last_stride = win_stride;
+    return UWSPR_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *uwspr_b200_status_string(int status)
+{
+    switch (status) {
+    case UWSPR_B200_OK: return "ok";
+    case UWSPR_B200_E_PARAM: return "parameter outside the supported domain";
+    case UWSPR_B200_E_CUDA: return "CUDA error";
+    case UWSPR_B200_E_CAPACITY: return "candidate capacity exceeded";
+    case UWSPR_B200_E_NOMEM: return "out of memory";
+    case UWSPR_B200_E_STATE: return "call sequence error";
+    default: return "unknown status";
+    }
+}
+
+const char *uwspr_b200_last_error(const uwspr_b200_ctx *ctx)
+{
+    static const char *none = "";
+    static std::string create_err;
+    (void)create_err;
+    return ctx ? ctx->err.c_str() : none;
+}
+
+static std::string g_create_error;
+UWSPR_B200_API const char *uwspr_b200_create_error(void) { return g_create_error.c_str(); }
+
+int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_out)
+{
+    if (!params || !ctx_out) return UWSPR_B200_E_PARAM;
+    *ctx_out = nullptr;
+    uwspr_b200_ctx *ctx = new uwspr_b200_ctx();
+    ctx->prm = *params;
+    auto bail = [&](int st) {
+        g_create_error = ctx->err;
+        uwspr_b200_destroy(ctx);
+        return st;
+    };
+    const uwspr_b200_params_t &p = ctx->prm;
+    // domain of the reference's own constants
+    if (p.spb != 256) return bail(fail(ctx, UWSPR_B200_E_PARAM, "spb must be 256 (the fine stage of the reference hard-codes 256 samples per symbol)"));
+    if (p.fl != UW_NP) return bail(fail(ctx, UWSPR_B200_E_PARAM, "fl must be 45000 (npoints is a literal in the reference)"));
+    if (p.fs <= 0 || p.maxfreqs < 1 || p.maxdrift < 0 || p.halfbandwidth < 1)
+        return bail(fail(ctx, UWSPR_B200_E_PARAM, "fs, maxfreqs, halfbandwidth must be positive and maxdrift non-negative"));
+    if (p.halfbandwidth > (int)((float)p.fs / 2.0))  // FDR_impl.cc:82-90 (the reference exits)
+        return bail(fail(ctx, UWSPR_B200_E_PARAM, "half pass bandwidth must be lower than the max frequency range"));
+    std::vector<uint32_t> off4;
+    std::vector<short> hyp_unique;
+    int rc = build_tables(ctx, off4, hyp_unique);
+    if (rc) return bail(rc);
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return bail(fail(ctx, UWSPR_B200_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce)));
+    if (p.device < 0 || p.device >= ndev) return bail(fail(ctx, UWSPR_B200_E_PARAM, "device ordinal out of range"));
+    ctx->device = p.device;
+#define CUC(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return bail(fail(ctx, UWSPR_B200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+    CUC(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    UwDims &d = ctx->d;
+    ctx->max_windows = p.max_windows > 0 ? p.max_windows : 1;
+    ctx->chunk_windows = std::min(ctx->max_windows, 2048);
+    const long long def_cap = (long long)ctx->max_windows * d.maxcand;
+    ctx->max_candidates = p.max_candidates > 0 ? p.max_candidates : (int)std::min<long long>(def_cap, 1 << 22);
+    Buffers &b = ctx->b;
+    const size_t cw = (size_t)ctx->chunk_windows, cap = (size_t)ctx->max_candidates;
+    CUC(cudaMalloc(&b.amp, cw * d.n_rows * d.nbp * sizeof(float)));
+    CUC(cudaMalloc(&b.psavg, cw * d.nbp * sizeof(float)));
+    CUC(cudaMalloc(&b.peaks, cw * d.maxcand * sizeof(UwPeak)));
+    CUC(cudaMalloc(&b.items, cap * sizeof(UwItem)));
+    CUC(cudaMalloc(&b.cands, cap * sizeof(uwspr_b200_candidate_t)));
+    CUC(cudaMalloc(&b.refined, cap * sizeof(uwspr_b200_refined_t)));
+    CUC(cudaMalloc(&b.jig, cap * UWSPR_B200_NJIG * sizeof(uwspr_b200_jiggle_t)));
+    CUC(cudaMalloc(&b.soft, cap * UWSPR_B200_NJIG * UW_NSYM));
+    CUC(cudaMalloc(&b.counters, 8 * sizeof(int)));
+    CUC(cudaMemset(b.counters, 0, 8 * sizeof(int)));
+    // tables
+    std::vector<float> window(UW_FFT_N);
+    for (int i = 0; i < d.size; i++) window[i] = (float)sin((M_PI / (d.size - 1)) * i);  // FDR_impl.cc:103-105
+    std::vector<float2> tw(UW_FFT_N);
+    for (int t = 0; t < UW_FFT_N; t++) {
+        const double a = -2.0 * M_PI * t / UW_FFT_N;
+        tw[t] = make_float2((float)cos(a), (float)sin(a));
+    }
+    CUC(cudaMalloc(&b.window, UW_FFT_N * sizeof(float)));
+    CUC(cudaMalloc(&b.twiddle, UW_FFT_N * sizeof(float2)));
+    CUC(cudaMalloc(&b.off4, off4.size() * sizeof(uint32_t)));
+    CUC(cudaMalloc(&b.hyp_unique, hyp_unique.size() * sizeof(short)));
+    CUC(cudaMemcpy(b.window, window.data(), UW_FFT_N * sizeof(float), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(b.twiddle, tw.data(), UW_FFT_N * sizeof(float2), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(b.off4, off4.data(), off4.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(b.hyp_unique, hyp_unique.data(), hyp_unique.size() * sizeof(short), cudaMemcpyHostToDevice));
+    CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; q++) {
+        CUC(cudaEventCreateWithFlags(&ctx->ev_h2d[q], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ctx->ev_free[q], cudaEventDisableTiming));
+    }
+    CUC(cudaEventCreate(&ctx->ev_begin));
+    CUC(cudaEventCreate(&ctx->ev_end));
+    if (uw_coarse_setup(d) || uw_fine_setup())
+        return bail(fail(ctx, UWSPR_B200_E_CUDA, "cannot reserve shared memory for the kernels (not an sm_100a device?)"));
+    ctx->grid_coarse = ctx->sm_count * uw_coarse_blocks_per_sm(d);
+    ctx->grid_fine = ctx->sm_count * uw_fine_blocks_per_sm();
+    CUC(cudaDeviceSynchronize());
+#undef CUC
+    *ctx_out = ctx;
+    return UWSPR_B200_OK;
+}
+
+void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    Buffers &b = ctx->b;
+    void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
+                     b.cands, b.refined, b.jig, b.soft, b.counters, b.window, b.twiddle, b.off4, b.hyp_unique };
+    for (void *q : ptrs)
+        if (q) cudaFree(q);
+    for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    for (int q = 0; q < 2; q++) {
+        if (ctx->ev_h2d[q]) cudaEventDestroy(ctx->ev_h2d[q]);
+        if (ctx->ev_free[q]) cudaEventDestroy(ctx->ev_free[q]);
+    }
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->compute && ctx->own_compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    delete ctx;
+}
+
+int uwspr_b200_info(const uwspr_b200_ctx *ctx, uwspr_b200_info_t *info)
+{
+    if (!ctx || !info) return UWSPR_B200_E_PARAM;
+    const UwDims &d = ctx->d;
+    info->size = d.size;
+    info->m = d.m;
+    info->hpbm = d.hpbm;
+    info->n_rows = d.n_rows;
+    info->finpb = d.finpb;
+    info->noiseidx = d.noiseidx;
+    info->df = d.df;
+    info->min_snr = d.min_snr;
+    info->bin_lo = d.bin_lo;
+    info->n_bins = d.n_bins;
+    info->n_lin = d.n_lin;
+    info->n_unique = d.n_unique;
+    info->max_cand_per_window = d.maxcand;
+    info->max_windows = ctx->max_windows;
+    info->max_candidates = ctx->max_candidates;
+    info->sm_count = ctx->sm_count;
+    return UWSPR_B200_OK;
+}
+
+int uwspr_b200_coarse(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin,
+                      int32_t *npk, uwspr_b200_candidate_t *cands, int cap, int32_t *total)
+{
+    return run(ctx, samples, space, win_stride, nwin, true, false, nullptr, nullptr, 0, 0, 0, npk, cands, cap, total,
+               nullptr, nullptr, nullptr);
+}
+
+int uwspr_b200_fine(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin,
+                    const int32_t *npk, const uwspr_b200_candidate_t *cands, int total, int jig_first,
+                    int jig_count, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft)
+{
+    return run(ctx, samples, space, win_stride, nwin, false, true, npk, cands, total, jig_first, jig_count, nullptr,
+               nullptr, 0, nullptr, refined, jig, soft);
+}
+
+int uwspr_b200_coarse_fine(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin,
+                           int jig_first, int jig_count, int32_t *npk, uwspr_b200_candidate_t *cands, int cap,
+                           int32_t *total, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft)
+{
+    return run(ctx, samples, space, win_stride, nwin, true, true, nullptr, nullptr, 0, jig_first, jig_count, npk, cands,
+               cap, total, refined, jig, soft);
+}
+
+int uwspr_b200_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return UWSPR_B200_E_PARAM;
+    return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? UWSPR_B200_OK : UWSPR_B200_E_NOMEM;
+}
+
+void uwspr_b200_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
+UWSPR_B200_API int uwspr_b200_set_debug(uwspr_b200_ctx *ctx, int keep_power)
+{
+    if (!ctx) return UWSPR_B200_E_PARAM;
+    CU(cudaSetDevice(ctx->device));
+    if (keep_power && !ctx->b.ps_dbg)
+        CU(cudaMalloc(&ctx->b.ps_dbg, (size_t)ctx->chunk_windows * ctx->d.n_rows * ctx->d.nbp * sizeof(float)));
+    ctx->debug_ps = keep_power != 0;
+    return UWSPR_B200_OK;
+}
+
+/* use the caller's CUDA stream (a cudaStream_t passed as void*) for all kernels, so that
+ * events recorded by the caller on that stream bracket the work; NULL restores the
+ * context's own stream */
+UWSPR_B200_API int uwspr_b200_set_stream(uwspr_b200_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return UWSPR_B200_E_PARAM;
+    static_assert(sizeof(void *) == sizeof(cudaStream_t), "stream handle size");
+    if (cuda_stream) {
+        if (ctx->own_compute && ctx->compute) cudaStreamDestroy(ctx->compute);
+        ctx->compute = (cudaStream_t)cuda_stream;
+        ctx->own_compute = false;
+    } else if (!ctx->own_compute) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+        ctx->own_compute = true;
+    }
+    return UWSPR_B200_OK;
+}
+
+int uwspr_b200_debug_spectrogram(uwspr_b200_ctx *ctx, int win, float *ps, float *psavg)
+{
+    if (!ctx) return UWSPR_B200_E_PARAM;
+    if (!ctx->debug_ps || !ctx->b.ps_dbg) return fail(ctx, UWSPR_B200_E_STATE, "enable uwspr_b200_set_debug first");
+    if (win < 0 || win >= ctx->last_nwin || win >= ctx->chunk_windows)
+        return fail(ctx, UWSPR_B200_E_PARAM, "window not in the last (single-chunk) call");
+    CU(cudaSetDevice(ctx->device));
+    const UwDims &d = ctx->d;
+    std::vector<float> tmp((size_t)d.n_rows * d.nbp);
+    if (ps) {
+        CU(cudaMemcpy(tmp.data(), ctx->b.ps_dbg + (size_t)win * d.n_rows * d.nbp, tmp.size() * sizeof(float),
+                      cudaMemcpyDeviceToHost));
+        for (int r = 0; r < d.n_rows; r++) memcpy(ps + (size_t)r * d.n_bins, &tmp[(size_t)r * d.nbp], sizeof(float) * d.n_bins);
+    }
+    if (psavg) CU(cudaMemcpy(psavg, ctx->b.psavg + (size_t)win * d.nbp, sizeof(float) * d.n_bins, cudaMemcpyDeviceToHost));
+    return UWSPR_B200_OK;
+}
+
+int uwspr_b200_last_timing(const uwspr_b200_ctx *ctx, float ms[4])
+{
+    if (!ctx || !ms) return UWSPR_B200_E_PARAM;
+    for (int q = 0; q < 4; q++) ms[q] = ctx->ms[q];
+    return UWSPR_B200_OK;
+}
+
+int64_t uwspr_b200_launch_count(const uwspr_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

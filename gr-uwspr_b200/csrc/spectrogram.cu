@@ -1,0 +1,296 @@
+// Kernel 1: half-symbol-step spectrogram + normalizer + peak pick for a batch of windows.
+//
+// Replaces, per window, lib/FDR_impl.cc:222-319 of the reference:
+//   :222-254  348 half-sine-windowed 512-point forward DFTs at a 128-sample hop, |X|^2,
+//             fft-shift
+//   :257-263  column sums psavg[j] (sequential over rows, fp32)
+//   :265-291  +-3-bin smoothing, 30th-percentile noise floor, SNR normalisation and clamp
+//   :293-306  strict local maxima -> candidate frequencies
+//   :309-319  stable descending sort on snr
+//
+// One CTA (256 threads) per window.  Four 64-thread groups each run one radix-8x8x8
+// Stockham FFT per iteration (87 iterations cover the 348 rows); the two inter-pass
+// exchanges go through shared memory, the window and twiddles live in registers / shared
+// memory.  Only the bins the rest of the path can touch are kept ([bin_lo, bin_lo+n_bins),
+// 42 of 512 at halfbandwidth 10): their amplitudes sqrt(ps) are written once to HBM for
+// the coarse-search kernel (powersum() takes the sqrt of every ps it reads,
+// FDR_impl.cc:199-205; IEEE sqrtf is deterministic, so hoisting it is exact), and their
+// powers are summed per column in row order by one owner thread per bin.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kGroups = 4;
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// multiply by -i
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// 8-point forward DFT, natural order in and out
+__device__ __forceinline__ void fft8(float2 *v)
+{
+    const float h = 0.70710678118654752440f;
+    float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    float2 a1 = cadd(v[1], v[5]), t5 = csub(v[1], v[5]);
+    float2 a2 = cadd(v[2], v[6]), t6 = csub(v[2], v[6]);
+    float2 a3 = cadd(v[3], v[7]), t7 = csub(v[3], v[7]);
+    float2 a5 = make_float2((t5.x + t5.y) * h, (t5.y - t5.x) * h);   // * exp(-i pi/4)
+    float2 a6 = mul_mi(t6);                                           // * exp(-i pi/2)
+    float2 a7 = make_float2((t7.y - t7.x) * h, -(t7.x + t7.y) * h);  // * exp(-3i pi/4)
+    float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_mi(csub(a1, a3));
+    float2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_mi(csub(a5, a7));
+    v[0] = cadd(b0, b1);
+    v[4] = csub(b0, b1);
+    v[2] = cadd(b2, b3);
+    v[6] = csub(b2, b3);
+    v[1] = cadd(b4, b5);
+    v[5] = csub(b4, b5);
+    v[3] = cadd(b6, b7);
+    v[7] = csub(b6, b7);
+}
+
+struct __align__(16) SpecSmem {
+    float2 buf[kGroups][UW_FFT_N];   // inter-pass exchange, one FFT per group
+    float2 tw[UW_FFT_N];             // exp(-2 pi i t / 512)
+    float psrow[kGroups][UW_FFT_N];  // powers of the kept bins of the four rows of this iteration
+    float psavg[UW_FFT_N];           // column sums of the kept bins
+    float smspec[UW_FFT_N];          // smoothed / normalised spectrum, finpb entries
+    float noise;
+    int npk;
+    UwPeak peaks[256];
+    UwPeak sorted[256];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int nwin,
+              const float *__restrict__ window, const float2 *__restrict__ twiddle,
+              float *__restrict__ amp, float *__restrict__ ps_dbg, float *__restrict__ psavg_out,
+              UwPeak *__restrict__ peaks_out, int *__restrict__ npk_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SpecSmem &sm = *reinterpret_cast<SpecSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int g = tid >> 6, j = tid & 63;
+    const int win = blockIdx.x;
+    if (win >= nwin) return;
+    const float2 *xw = x + (long long)win * win_stride;
+
+    for (int t = tid; t < UW_FFT_N; t += kThreads) sm.tw[t] = twiddle[t];
+    float wj[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) wj[r] = window[j + 64 * r];
+
+    // this thread owns the column sums of kept bins tid and tid+256
+    float acc0 = 0.0f, acc1 = 0.0f;
+    const int nb = d.n_bins;
+    __syncthreads();
+
+    const int n_iter = (d.n_rows + kGroups - 1) / kGroups;
+    for (int it = 0; it < n_iter; it++) {
+        const int row = it * kGroups + g;
+        const bool live = row < d.n_rows;
+        float2 v[8];
+        if (live) {
+            const float2 *src = xw + (long long)row * UW_HOP + j;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float2 s = __ldg(src + 64 * r);
+                // FDR_impl.cc:230-231: the fp32 sample times the fp32 window, rounded once
+                v[r] = make_float2(__fmul_rn(s.x, wj[r]), __fmul_rn(s.y, wj[r]));
+            }
+            // pass 0 (Ns = 1): no twiddles; out[8j + r] = X[r]
+            fft8(v);
+#pragma unroll
+            for (int r = 0; r < 8; r++) sm.buf[g][8 * j + r] = v[r];
+        }
+        __syncthreads();
+        if (live) {
+            // pass 1 (Ns = 8)
+            const int k = j & 7;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float2 s = sm.buf[g][j + 64 * r];
+                v[r] = (r == 0) ? s : cmul(s, sm.tw[8 * r * k]);
+            }
+            fft8(v);
+        }
+        __syncthreads();
+        if (live) {
+            const int j0 = (j >> 3) * 64 + (j & 7);
+#pragma unroll
+            for (int r = 0; r < 8; r++) sm.buf[g][j0 + 8 * r] = v[r];
+        }
+        __syncthreads();
+        if (live) {
+            // pass 2 (Ns = 64): thread j ends with X[j + 64 r]
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float2 s = sm.buf[g][j + 64 * r];
+                v[r] = (r == 0) ? s : cmul(s, sm.tw[r * j]);
+            }
+            fft8(v);
+            float *amp_row = amp + ((long long)win * d.n_rows + row) * d.nbp;
+            float *dbg_row = ps_dbg ? ps_dbg + ((long long)win * d.n_rows + row) * d.nbp : nullptr;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int kbin = j + 64 * r;                 // FFT bin (0 = DC)
+                const int sh = (kbin + UW_FFT_N / 2) & (UW_FFT_N - 1);  // index after the shift of :247-248
+                const int c = sh - d.bin_lo;
+                if (c >= 0 && c < nb) {
+                    // :252 ps = re*re + im*im, three roundings
+                    float p = __fadd_rn(__fmul_rn(v[r].x, v[r].x), __fmul_rn(v[r].y, v[r].y));
+                    sm.psrow[g][c] = p;
+                    amp_row[c] = __fsqrt_rn(p);
+                    if (dbg_row) dbg_row[c] = p;
+                }
+            }
+        }
+        __syncthreads();
+        // :257-263 column sums in row order
+        {
+            const int rows_here = min(kGroups, d.n_rows - it * kGroups);
+            if (tid < nb)
+                for (int q = 0; q < rows_here; q++) acc0 = __fadd_rn(acc0, sm.psrow[q][tid]);
+            if (tid + kThreads < nb)
+                for (int q = 0; q < rows_here; q++) acc1 = __fadd_rn(acc1, sm.psrow[q][tid + kThreads]);
+        }
+        // psrow is rewritten only after the next iteration's three barriers
+    }
+    if (tid < nb) sm.psavg[tid] = acc0;
+    if (tid + kThreads < nb) sm.psavg[tid + kThreads] = acc1;
+    __syncthreads();
+    if (psavg_out) {
+        for (int c = tid; c < nb; c += kThreads) psavg_out[(long long)win * d.nbp + c] = sm.psavg[c];
+    }
+
+    // :265-275 smoothing over +-3 bins, accumulated in the order j = -3..3 from 0.0f
+    const int base = d.m - d.hpbm - d.bin_lo;  // kept-bin index of shifted bin m-hpbm
+    for (int i = tid; i < d.finpb; i += kThreads) {
+        float a = 0.0f;
+#pragma unroll
+        for (int q = -3; q <= 3; q++) a = __fadd_rn(a, sm.psavg[base + i + q]);
+        sm.smspec[i] = a;
+    }
+    __syncthreads();
+    // :277-285 the noiseidx-th smallest value (qsort + pick), found by rank counting;
+    // ties are broken by index so exactly one element has each rank
+    for (int i = tid; i < d.finpb; i += kThreads) {
+        const float vi = sm.smspec[i];
+        int rank = 0;
+        for (int q = 0; q < d.finpb; q++) {
+            const float vq = sm.smspec[q];
+            rank += (vq < vi) || (vq == vi && q < i);
+        }
+        if (rank == d.noiseidx) sm.noise = vi;
+    }
+    __syncthreads();
+    const float noise = sm.noise;
+    __syncthreads();
+    // :287-291
+    for (int i = tid; i < d.finpb; i += kThreads) {
+        float q = __fdiv_rn(sm.smspec[i], noise);
+        float s = __fsub_rn(q, 1.0f);  // (double)q - 1.0 stored to float == fp32 subtraction
+        if (s < d.min_snr) s = d.floor_val;
+        sm.psrow[0][i] = s;  // reuse as the normalised spectrum
+    }
+    __syncthreads();
+    // :293-306 strict local maxima, first maxfreqs in bin order.  One thread walks the
+    // (short) pass band so that the order and the cap are exactly the reference's.
+    if (tid == 0) {
+        int n = 0;
+        const float *s = sm.psrow[0];
+        for (int i = 1; i < d.finpb - 1; i++) {
+            if (s[i] > s[i - 1] && s[i] > s[i + 1] && n < d.maxcand) {
+                sm.peaks[n].freq = __fmul_rn((float)(i - d.hpbm), d.df);
+                // 10*log10f(x): evaluated in double and rounded, then the fp32 product
+                sm.peaks[n].snr = __fmul_rn(10.0f, (float)log10((double)s[i]));
+                n++;
+            }
+        }
+        sm.npk = n;
+    }
+    __syncthreads();
+    const int npk = sm.npk;
+    // :311-319 stable descending sort: rank = #greater + #equal before
+    if (tid < npk) {
+        const float si = sm.peaks[tid].snr;
+        int rank = 0;
+        for (int q = 0; q < npk; q++) {
+            const float sq = sm.peaks[q].snr;
+            rank += (sq > si) || (sq == si && q < tid);
+        }
+        sm.sorted[rank] = sm.peaks[tid];
+    }
+    __syncthreads();
+    if (tid < npk) peaks_out[(long long)win * d.maxcand + tid] = sm.sorted[tid];
+    if (tid == 0) npk_out[win] = npk;
+}
+
+// Exclusive scan of npk over the windows of one chunk + expansion into the compact work
+// list.  counters: [0] running total over the chunks of this call (in/out), [1] overflow
+// flag, [2] coarse ticket, [3] fine ticket, [4] first item of this chunk.  Item indices are
+// global to the call (so results land compactly, window-major); item.win is relative to
+// the chunk.
+__global__ void __launch_bounds__(1024)
+k_worklist(const int *__restrict__ npk, int nwin, int cap, int *__restrict__ base,
+           UwItem *__restrict__ items, int *__restrict__ counters)
+{
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int run0 = counters[0];
+    const int per = (nwin + 1023) / 1024;
+    const int lo = min(nwin, tid * per), hi = min(nwin, lo + per);
+    int s = 0;
+    for (int w = lo; w < hi; w++) s += npk[w];
+    part[tid] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partial sums
+    for (int off = 1; off < 1024; off <<= 1) {
+        int v = (tid >= off) ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int run = run0 + part[tid] - s;
+    for (int w = lo; w < hi; w++) {
+        base[w] = run;
+        const int n = npk[w];
+        for (int q = 0; q < n; q++)
+            if (run + q < cap) {
+                items[run + q].win = w;
+                items[run + q].slot = q;
+            }
+        run += n;
+    }
+    if (tid == 1023) {
+        const int end = run0 + part[1023];
+        counters[0] = end;
+        if (end > cap) counters[1] = 1;
+        counters[2] = run0;
+        counters[3] = run0;
+        counters[4] = run0;
+    }
+}
+
+}  // namespace
+
+void uw_launch_spectrogram(const UwDims &d, const float2 *x, long long win_stride, int nwin,
+                           const float *window, const float2 *twiddle, float *amp, float *ps_dbg,
+                           float *psavg, UwPeak *peaks, int *npk, cudaStream_t s)
+{
+    static_assert(sizeof(SpecSmem) <= 48 * 1024, "spectrogram shared memory must fit the default limit");
+    k_spectrogram<<<nwin, kThreads, sizeof(SpecSmem), s>>>(d, x, win_stride, nwin, window, twiddle, amp, ps_dbg,
+                                                           psavg, peaks, npk);
+}
+
+void uw_launch_worklist(const int *npk, int nwin, int cap, int *base, UwItem *items, int *counters,
+                        cudaStream_t s)
+{
+    k_worklist<<<1, 1024, 0, s>>>(npk, nwin, cap, base, items, counters);
+}

@@ -1,0 +1,297 @@
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+NSYM = 162
+NJIG = 17
+HOST, DEVICE = 0, 1
+
+# every symbol include/uwspr_b200.h declares
+EXPORTED_SYMBOLS = [
+    "uwspr_b200_create", "uwspr_b200_destroy", "uwspr_b200_last_error", "uwspr_b200_status_string",
+    "uwspr_b200_create_error", "uwspr_b200_info", "uwspr_b200_coarse", "uwspr_b200_fine", "uwspr_b200_coarse_fine",
+    "uwspr_b200_deinterleave", "uwspr_b200_fano", "uwspr_b200_decode_candidate", "uwspr_b200_host_alloc",
+    "uwspr_b200_host_free", "uwspr_b200_set_stream", "uwspr_b200_set_debug", "uwspr_b200_debug_spectrogram",
+    "uwspr_b200_last_timing", "uwspr_b200_launch_count",
+]
+
+CAND_DTYPE = np.dtype(
+    {
+        # candidate_t of the reference (lib/candidate_t.h:27-50)
+        "names": ["freq", "snr", "drift", "sync", "shift", "m_type", "lin_drift", "V1", "V2", "p1", "p2"],
+        "formats": ["<f4", "<f4", "<f4", "<f4", "<i4", "<i4", "<f4", "<f8", "<f8", "<i4", "<i4"],
+        "offsets": [0, 4, 8, 12, 16, 20, 24, 24, 32, 40, 44],
+        "itemsize": 48,
+    }
+)
+REFINED_DTYPE = np.dtype([("f1", "<f4"), ("shift1", "<i4"), ("drift1", "<f4"), ("sync1", "<f4"), ("worth_a_try", "<i4"), ("reserved", "<i4")])
+JIG_DTYPE = np.dtype([("sync", "<f4"), ("rms", "<f4"), ("shift", "<i4"), ("gate", "<i4")])
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "fs", "fl", "spb", "maxdrift", "maxfreqs", "halfbandwidth", "cf", "threshold",
+        "device", "max_windows", "max_candidates", "nonlinear_intended_t")]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("size", C.c_int32), ("m", C.c_int32), ("hpbm", C.c_int32), ("n_rows", C.c_int32), ("finpb", C.c_int32),
+        ("noiseidx", C.c_int32), ("df", C.c_float), ("min_snr", C.c_float), ("bin_lo", C.c_int32), ("n_bins", C.c_int32),
+        ("n_lin", C.c_int32), ("n_unique", C.c_int32), ("max_cand_per_window", C.c_int32), ("max_windows", C.c_int32),
+        ("max_candidates", C.c_int32), ("sm_count", C.c_int32),
+    ]
+
+
+class UwsprError(RuntimeError):
+    def __init__(self, status, text):
+        super().__init__("uwspr_b200 status %d: %s" % (status, text))
+        self.status = status
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(_HERE), "libuwspr_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """loads the in-tree CUDA library; raises if it has not been built (no fallback)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise UwsprError(-1, "libuwspr_b200.so is not built (run __graft_entry__.build() or make -C gr-uwspr_b200); "
+                             "there is no CPU fallback for the CUDA path")
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.uwspr_b200_create.restype = C.c_int
+    L.uwspr_b200_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.uwspr_b200_destroy.argtypes = [vp]
+    L.uwspr_b200_last_error.restype = C.c_char_p
+    L.uwspr_b200_last_error.argtypes = [vp]
+    L.uwspr_b200_status_string.restype = C.c_char_p
+    L.uwspr_b200_status_string.argtypes = [C.c_int]
+    L.uwspr_b200_create_error.restype = C.c_char_p
+    L.uwspr_b200_info.restype = C.c_int
+    L.uwspr_b200_info.argtypes = [vp, C.POINTER(Info)]
+    L.uwspr_b200_coarse.restype = C.c_int
+    L.uwspr_b200_coarse.argtypes = [vp, vp, C.c_int, i64, C.c_int, vp, vp, C.c_int, vp]
+    L.uwspr_b200_fine.restype = C.c_int
+    L.uwspr_b200_fine.argtypes = [vp, vp, C.c_int, i64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.uwspr_b200_coarse_fine.restype = C.c_int
+    L.uwspr_b200_coarse_fine.argtypes = [vp, vp, C.c_int, i64, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.uwspr_b200_deinterleave.argtypes = [vp]
+    L.uwspr_b200_fano.restype = C.c_int
+    L.uwspr_b200_fano.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_uint32]
+    L.uwspr_b200_decode_candidate.restype = C.c_int
+    L.uwspr_b200_decode_candidate.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.uwspr_b200_host_alloc.restype = C.c_int
+    L.uwspr_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.uwspr_b200_host_free.argtypes = [vp]
+    L.uwspr_b200_set_stream.restype = C.c_int
+    L.uwspr_b200_set_stream.argtypes = [vp, vp]
+    L.uwspr_b200_set_debug.restype = C.c_int
+    L.uwspr_b200_set_debug.argtypes = [vp, C.c_int]
+    L.uwspr_b200_debug_spectrogram.restype = C.c_int
+    L.uwspr_b200_debug_spectrogram.argtypes = [vp, C.c_int, vp, vp]
+    L.uwspr_b200_last_timing.restype = C.c_int
+    L.uwspr_b200_last_timing.argtypes = [vp, vp]
+    L.uwspr_b200_launch_count.restype = i64
+    L.uwspr_b200_launch_count.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _samples_arg(samples):
+    """accepts a numpy complex64 array (host) or (device_pointer:int, n_complex:int) for device memory"""
+    if isinstance(samples, tuple):
+        return C.c_void_p(int(samples[0])), DEVICE, None
+    a = np.ascontiguousarray(samples, dtype=np.complex64)
+    return _p(a), HOST, a
+
+
+class Context:
+    """one uwspr_b200_ctx: both blocks' arithmetic for batches of windows on one GPU"""
+
+    def __init__(self, fs=375, fl=45000, spb=256, maxdrift=0, maxfreqs=200, halfbandwidth=10, cf=1500, threshold=10,
+                 device=0, max_windows=1, max_candidates=0, nonlinear_intended_t=0):
+        self.L = load_library()
+        self.prm = Params(fs, fl, spb, maxdrift, maxfreqs, halfbandwidth, cf, threshold, device, max_windows,
+                          max_candidates, nonlinear_intended_t)
+        h = C.c_void_p()
+        st = self.L.uwspr_b200_create(C.byref(self.prm), C.byref(h))
+        if st != 0:
+            raise UwsprError(st, self.L.uwspr_b200_create_error().decode() or self.L.uwspr_b200_status_string(st).decode())
+        self.h = h
+        self.fl = fl
+        inf = Info()
+        self._check(self.L.uwspr_b200_info(self.h, C.byref(inf)))
+        self.info = inf
+
+    def _check(self, st):
+        if st != 0:
+            raise UwsprError(st, self.L.uwspr_b200_last_error(self.h).decode() or self.L.uwspr_b200_status_string(st).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.uwspr_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.L.uwspr_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def set_debug(self, on=True):
+        self._check(self.L.uwspr_b200_set_debug(self.h, int(on)))
+
+    def _nwin(self, samples, nwin, stride):
+        if nwin is not None:
+            return nwin
+        a = np.asarray(samples)
+        if a.ndim == 2:
+            return a.shape[0]
+        return 1 + (a.size - self.fl) // stride
+
+    # ---- FDR_impl::transform for a batch --------------------------------------------------
+    def coarse(self, samples, nwin=None, stride=None, fetch=True):
+        stride = self.fl if stride is None else stride
+        ptr, space, keep = _samples_arg(samples)
+        nwin = self._nwin(samples, nwin, stride) if not isinstance(samples, tuple) else nwin
+        cap = self.info.max_candidates
+        npk = np.zeros(nwin, np.int32) if fetch else None
+        cands = np.zeros(cap, CAND_DTYPE) if fetch else None
+        total = C.c_int32(0)
+        self._check(self.L.uwspr_b200_coarse(self.h, ptr, space, stride, nwin, _p(npk), _p(cands), cap, C.byref(total)))
+        if not fetch:
+            return total.value
+        return npk, cands[: total.value].copy()
+
+    # ---- demodulate() up to the decoder ---------------------------------------------------
+    def fine(self, samples, npk=None, cands=None, nwin=None, stride=None, jig_first=0, jig_count=NJIG, fetch=True):
+        stride = self.fl if stride is None else stride
+        ptr, space, keep = _samples_arg(samples)
+        nwin = self._nwin(samples, nwin, stride) if not isinstance(samples, tuple) else nwin
+        if cands is not None:
+            cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+            npk = np.ascontiguousarray(npk, dtype=np.int32)
+            total = len(cands)
+        else:
+            total = 0
+        n_out = total if cands is not None else self.info.max_candidates
+        refined = np.zeros(n_out, REFINED_DTYPE) if fetch else None
+        jig = np.zeros((n_out, jig_count), JIG_DTYPE) if fetch else None
+        soft = np.zeros((n_out, jig_count, NSYM), np.uint8) if fetch else None
+        self._check(self.L.uwspr_b200_fine(self.h, ptr, space, stride, nwin, _p(npk), _p(cands), total, jig_first,
+                                           jig_count, _p(refined), _p(jig), _p(soft)))
+        return refined, jig, soft
+
+    def coarse_fine(self, samples, nwin=None, stride=None, jig_first=0, jig_count=NJIG, fetch=True):
+        stride = self.fl if stride is None else stride
+        ptr, space, keep = _samples_arg(samples)
+        nwin = self._nwin(samples, nwin, stride) if not isinstance(samples, tuple) else nwin
+        cap = self.info.max_candidates
+        total = C.c_int32(0)
+        if not fetch:
+            self._check(self.L.uwspr_b200_coarse_fine(self.h, ptr, space, stride, nwin, jig_first, jig_count, None, None,
+                                                      0, C.byref(total), None, None, None))
+            return total.value
+        npk = np.zeros(nwin, np.int32)
+        cands = np.zeros(cap, CAND_DTYPE)
+        refined = np.zeros(cap, REFINED_DTYPE)
+        jig = np.zeros((cap, jig_count), JIG_DTYPE)
+        soft = np.zeros((cap, jig_count, NSYM), np.uint8)
+        self._check(self.L.uwspr_b200_coarse_fine(self.h, ptr, space, stride, nwin, jig_first, jig_count, _p(npk),
+                                                  _p(cands), cap, C.byref(total), _p(refined), _p(jig), _p(soft)))
+        t = total.value
+        return npk, cands[:t].copy(), refined[:t].copy(), jig[:t].copy(), soft[:t].copy()
+
+    def debug_spectrogram(self, win=0):
+        ps = np.zeros((self.info.n_rows, self.info.n_bins), np.float32)
+        psavg = np.zeros(self.info.n_bins, np.float32)
+        self._check(self.L.uwspr_b200_debug_spectrogram(self.h, win, _p(ps), _p(psavg)))
+        return ps, psavg
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        self._check(self.L.uwspr_b200_last_timing(self.h, ms))
+        return [float(v) for v in ms]
+
+    def launch_count(self):
+        return int(self.L.uwspr_b200_launch_count(self.h))
+
+
+def deinterleave(sym):
+    s = np.array(sym, dtype=np.uint8, copy=True)
+    load_library().uwspr_b200_deinterleave(_p(s))
+    return s
+
+
+def fano(symbols, delta=60, maxcycles=10000, nbits=81):
+    s = np.ascontiguousarray(symbols, dtype=np.uint8)
+    data = np.zeros(11, np.uint8)
+    metric, cycles, maxnp = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    r = load_library().uwspr_b200_fano(C.byref(metric), C.byref(cycles), C.byref(maxnp), _p(data), _p(s), nbits, delta, maxcycles)
+    return r, data, metric.value, cycles.value, maxnp.value
+
+
+def decode_candidates(refined, jig, soft):
+    """the peak-up/decode loop (sync_and_demodulate_impl.cc:457-490) over fetched results;
+    returns a list of (candidate index, 7-byte message, idt used)"""
+    L = load_library()
+    out = []
+    jig = np.ascontiguousarray(jig)
+    soft = np.ascontiguousarray(soft)
+    refined = np.ascontiguousarray(refined)
+    for g in range(len(refined)):
+        msg = np.zeros(7, np.int8)
+        idt, cyc = C.c_int32(), C.c_uint32()
+        ok = L.uwspr_b200_decode_candidate(_p(refined[g:g + 1]), _p(jig[g]), _p(soft[g]), jig.shape[1], _p(msg),
+                                           C.byref(idt), C.byref(cyc))
+        if ok:
+            out.append((g, msg.view(np.uint8).copy(), idt.value))
+    return out
+
+
+class FDR:
+    """uwspr.FDR: same constructor arguments as the reference block (include/uwspr/FDR.h:49-50).
+    transform(window) -> candidate array, as FDR_impl::transform publishes it."""
+
+    def __init__(self, fs, fl, spb, maxdrift, maxfreqs, halfbandwidth, cf, threshold, device=0, max_windows=1, ctx=None):
+        self.ctx = ctx or Context(fs, fl, spb, maxdrift, maxfreqs, halfbandwidth, cf, threshold, device=device,
+                                  max_windows=max_windows)
+
+    def transform(self, window):
+        npk, cands = self.ctx.coarse(np.asarray(window).reshape(1, -1))
+        return cands
+
+
+class sync_and_demodulate:
+    """uwspr.sync_and_demodulate (include/uwspr/sync_and_demodulate.h:49).
+    demodulate(window, candidates) -> list of 7-byte messages, one per decoded candidate, in
+    candidate order (sync_and_demodulate_impl.cc:389-531)."""
+
+    def __init__(self, fs, fl, spb, maxdrift, maxfreqs, cf, device=0, ctx=None):
+        self.ctx = ctx or Context(fs, fl, spb, maxdrift, maxfreqs, 10, cf, 10, device=device, max_windows=1,
+                                  max_candidates=max(1, maxfreqs))
+
+    def demodulate(self, window, candidates):
+        cands = np.ascontiguousarray(candidates, dtype=CAND_DTYPE)
+        if len(cands) == 0:
+            return []
+        npk = np.array([len(cands)], np.int32)
+        refined, jig, soft = self.ctx.fine(np.asarray(window).reshape(1, -1), npk, cands)
+        return [m for _, m, _ in decode_candidates(refined, jig, soft)]

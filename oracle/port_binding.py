@@ -88,6 +88,8 @@ def lib():
         ]
         L.orc_demodulate.restype = C.c_int
         L.orc_demodulate.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int]
+        L.orc_demodulate_ex.restype = C.c_int
+        L.orc_demodulate_ex.argtypes = [C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp]
         L.orc_deinterleave.argtypes = [vp]
         L.orc_interleave.argtypes = [vp]
         L.orc_encode.argtypes = [vp, vp, C.c_uint]
@@ -191,6 +193,31 @@ def demodulate(x, cands, cf=1500, run_fano=True, max_calls=8192, max_fanos=4096)
     nb = L.orc_demodulate(cf, _p(x), x.size, _p(cands), len(cands), C.byref(tr), _p(blobs), len(blobs), int(run_fano))
     assert tr.n_calls <= max_calls and tr.n_fanos <= max_fanos
     return blobs[:nb].copy(), [calls[i] for i in range(tr.n_calls)], [fanos[i] for i in range(tr.n_fanos)]
+
+
+def demodulate_full(x, cands, cf=1500):
+    """every mode-2 evaluation of every gated candidate (decoder skipped, so all 17 jiggled
+    shifts run); returns (refined [npk,5] float32, list per candidate of the 17 mode-2 calls or [])"""
+    L = lib()
+    x = _iq(x)
+    cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+    max_calls = 32 * max(1, len(cands))
+    calls = (SdCall * max_calls)()
+    tr = Trace(calls, max_calls, 0, None, 0, 0)
+    refined = np.zeros((len(cands), 5), np.float32)
+    L.orc_demodulate_ex(cf, _p(x), x.size, _p(cands), len(cands), C.byref(tr), None, 0, 0, _p(refined))
+    assert tr.n_calls <= max_calls
+    per, k = [], 0
+    for j in range(len(cands)):
+        k += 2 + (2 if cands[j]["m_type"] == 0 else 0)
+        jigs = []
+        if refined[j, 4] != 0:
+            k += 2
+            jigs = [calls[k + t] for t in range(17)]
+            k += 17
+        per.append(jigs)
+    assert k == tr.n_calls
+    return refined, per
 
 
 def slm_frequency_drift(V1, V2, p1, p2, cf, t):

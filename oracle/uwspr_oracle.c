@@ -473,8 +473,19 @@ static void sd_call(orc_trace_t *tr, const orc_candidate_t *cand, int cf, const 
     trace_call(tr, &rec);
 }
 
+int orc_demodulate_ex(int cf, const float *iq, int fl, const orc_candidate_t *cands_in, int npk,
+                      orc_trace_t *trace, unsigned char *blobs, int max_blobs, int run_fano,
+                      float *refined /* [npk][5]: f1, shift1, drift1, sync1, worth_a_try at :457 */);
+
 int orc_demodulate(int cf, const float *iq, int fl, const orc_candidate_t *cands_in, int npk,
                    orc_trace_t *trace, unsigned char *blobs, int max_blobs, int run_fano)
+{
+    return orc_demodulate_ex(cf, iq, fl, cands_in, npk, trace, blobs, max_blobs, run_fano, NULL);
+}
+
+int orc_demodulate_ex(int cf, const float *iq, int fl, const orc_candidate_t *cands_in, int npk,
+                      orc_trace_t *trace, unsigned char *blobs, int max_blobs, int run_fano,
+                      float *refined)
 {
     /* tuning constants, sync_and_demodulate_impl.cc:326-335 */
     const unsigned int maxcycles = 10000;
@@ -539,6 +550,13 @@ int orc_demodulate(int cf, const float *iq, int fl, const orc_candidate_t *cands
             worth_a_try = 1;
         } else {
             worth_a_try = 0;
+        }
+        if (refined) {
+            refined[5 * j + 0] = f1;
+            refined[5 * j + 1] = (float)shift1;
+            refined[5 * j + 2] = drift1;
+            refined[5 * j + 3] = sync1;
+            refined[5 * j + 4] = (float)worth_a_try;
         }
         int idt = 0, not_decoded = 1;
         while (worth_a_try && not_decoded && idt <= (128 / iifac)) {        /* :460-482 */

@@ -78,9 +78,9 @@ float orc_slm_frequency_drift(double V1, double V2, int p1, int p2, float cf, fl
 /* lib/slm.cc:76-116: k-th trajectory of the generator, k in [0,125); returns 0 past the end */
 int orc_slm_trajectory(int k, double *V1, double *V2, int *p1, int *p2);
 
-/* lib/sync_and_demodulate_impl.cc:126-256.  nonlinear_t: value used for the
- * uninitialised `t` of the nonlinear branch (:177-180, hazard H1); the compiled
- * reference behaves as t == 0. */
+/* lib/sync_and_demodulate_impl.cc:126-256.  The uninitialised `t` of the nonlinear branch (:177-180, hazard H1); the compiled
+ * reference behaves as t == 0 (orc_set_nonlinear_intended_t(1) selects i*111/162). */
+void orc_set_nonlinear_intended_t(int on);
 void orc_sync_and_demodulate(const orc_candidate_t *cand, int cf, const float *id, const float *qd,
                              long np, unsigned char *symbols, float *f1, int ifmin, int ifmax,
                              float fstep, int *shift1, int lagmin, int lagmax, int lagstep,
@@ -121,6 +121,12 @@ typedef struct {
  * driver evaluate all 17 jiggled shifts of every gated candidate. */
 int orc_demodulate(int cf, const float *iq, int fl, const orc_candidate_t *cands, int npk,
                    orc_trace_t *trace, unsigned char *blobs, int max_blobs, int run_fano);
+
+/* same, also reporting per candidate f1, shift1, drift1, sync1, worth_a_try as they stand
+ * when the peak-up loop starts (:457); refined: [npk][5] floats or NULL */
+int orc_demodulate_ex(int cf, const float *iq, int fl, const orc_candidate_t *cands, int npk,
+                      orc_trace_t *trace, unsigned char *blobs, int max_blobs, int run_fano,
+                      float *refined);
 
 /* lib/sync_and_demodulate_impl.cc:265-282 */
 void orc_deinterleave(unsigned char *sym162);

@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Everything here needs a B200 (`-m gpu`).  Bars:
+  * spectrogram power: the FFT is the one unpinned piece (FFTW3f in the reference, a
+    double-precision DFT in the oracle): |ps - ps_oracle| <= 2e-6 * max(ps row) per row;
+  * everything after the FFT: bit exact.  The oracle's normalizer / coarse search is run on
+    the GPU's own ps (kept bins spliced into the oracle's full spectrogram) and every field
+    of every candidate must be identical, the sync metric included;
+  * fine sync / soft symbols: bit exact against the oracle on the same candidates
+    (f1, shift1, drift1, sync1, every jiggle's sync and all 162 soft symbols);
+  * end to end on the fixtures: same candidates (bin, shift, drift model) as the golden
+    reference run, sync within 1e-4 relative, decoded messages identical.
+"""
+import numpy as np
+import pytest
+
+from oracle import port_binding as ob
+from oracle import testdata as td
+from tests.conftest import case_window
+
+pytestmark = pytest.mark.gpu
+
+import uwspr_b200 as ub  # noqa: E402
+
+CASES = ["ve3emb_c2", "test_1500", "rec_150613", "mix_whales", "syn_m0_w0", "syn_m0_w1", "syn_m0_w2", "syn_m0_w3",
+         "syn_m0_w4", "syn_m0_w5", "syn_m4_w0", "syn_m4_w3", "syn_m4_w6", "syn_m4_w7"]
+
+_ctx_cache = {}
+
+
+def ctx_for(maxdrift=0, halfbandwidth=10, threshold=10, max_windows=64, **kw):
+    key = (maxdrift, halfbandwidth, threshold, max_windows, tuple(sorted(kw.items())))
+    if key not in _ctx_cache:
+        _ctx_cache[key] = ub.Context(maxdrift=maxdrift, halfbandwidth=halfbandwidth, threshold=threshold,
+                                     max_windows=max_windows, **kw)
+    return _ctx_cache[key]
+
+
+def cands_equal_exact(a, b):
+    return len(a) == len(b) and td.canon_cands(a).tobytes() == td.canon_cands(b).tobytes()
+
+
+def oracle_on_gpu_ps(of, ctx, x, win=0):
+    """oracle normalizer + coarse search fed with the GPU's power spectrogram"""
+    ps = of.spectrogram(x)
+    gps, gpsavg = ctx.debug_spectrogram(win)
+    lo, nb = ctx.info.bin_lo, ctx.info.n_bins
+    ps_o = ps[:, lo:lo + nb].copy()
+    ps[:, lo:lo + nb] = gps
+    c0, psavg, _ = of.normalize_peaks(ps)
+    return of.coarse(ps, c0), ps_o, gps, psavg[lo:lo + nb], gpsavg
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_coarse_against_oracle_and_golden(name, golden, golden_windows):
+    md = int(golden["case_maxdrift"][CASES.index(name)])
+    x = case_window(name, golden_windows)
+    ctx = ctx_for(maxdrift=md)
+    ctx.set_debug(True)
+    npk, cands = ctx.coarse(x.reshape(1, -1))
+    of = ob.OracleFDR(maxdrift=md)
+    want, ps_o, ps_g, psavg_o, psavg_g = oracle_on_gpu_ps(of, ctx, x)
+    # FFT-level agreement
+    tol = 2e-6 * ps_o.max(axis=1, keepdims=True) + 1e-30
+    assert np.all(np.abs(ps_g - ps_o) <= tol)
+    # column sums are sequential fp32 sums of the GPU's own ps: bit exact
+    assert np.array_equal(psavg_g, psavg_o)
+    # post-FFT chain: bit exact
+    assert npk[0] == len(want)
+    assert cands_equal_exact(cands, want)
+    # against the recorded reference run
+    ref = golden[name + "/cands"].view(ob.CAND_DTYPE).reshape(-1)
+    assert len(ref) == len(cands)
+    for a, b in zip(cands, ref):
+        assert a["freq"] == b["freq"] and a["shift"] == b["shift"] and a["m_type"] == b["m_type"]
+        if a["m_type"] == 0:
+            assert a["lin_drift"] == b["lin_drift"]
+        else:
+            assert (a["V1"], a["V2"], a["p1"], a["p2"]) == (b["V1"], b["V2"], b["p1"], b["p2"])
+        assert abs(a["sync"] - b["sync"]) <= 1e-4 * abs(b["sync"])
+        assert abs(a["snr"] - b["snr"]) <= 1e-4 * max(1.0, abs(b["snr"]))
+
+
+def check_fine_against_oracle(ctx, x, cands, cf=1500):
+    npk = np.array([len(cands)], np.int32)
+    refined, jig, soft = ctx.fine(x.reshape(1, -1), npk, cands)
+    o_ref, o_jigs = ob.demodulate_full(x, cands, cf=cf)
+    for g in range(len(cands)):
+        assert refined["f1"][g].tobytes() == o_ref[g, 0].tobytes()
+        assert refined["shift1"][g] == int(o_ref[g, 1])
+        assert refined["drift1"][g].tobytes() == o_ref[g, 2].tobytes()
+        assert refined["sync1"][g].tobytes() == o_ref[g, 3].tobytes()
+        assert refined["worth_a_try"][g] == int(o_ref[g, 4])
+        if not refined["worth_a_try"][g]:
+            assert not soft[g].any() and not jig["gate"][g].any()
+            continue
+        for t, call in enumerate(o_jigs[g]):
+            assert jig["shift"][g, t] == call.shift_in
+            assert jig["sync"][g, t].tobytes() == np.float32(call.sync_out).tobytes()
+            assert np.array_equal(soft[g, t], np.frombuffer(bytes(call.symbols), np.uint8))
+            y = soft[g, t].astype(np.float32) - 128.0
+            rms = np.float32(np.sqrt(np.float64(np.float32((y * y).sum())) / 162.0))
+            assert jig["rms"][g, t] == rms
+            assert jig["gate"][g, t] == int(call.sync_out > np.float32(0.12) and rms > np.float32(40.625))
+    return refined, jig, soft
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fine_bit_exact_and_messages(name, golden, golden_windows):
+    md = int(golden["case_maxdrift"][CASES.index(name)])
+    x = case_window(name, golden_windows)
+    ctx = ctx_for(maxdrift=md)
+    ref_cands = golden[name + "/cands"].view(ob.CAND_DTYPE).reshape(-1)
+    refined, jig, soft = check_fine_against_oracle(ctx, x, ref_cands)
+    msgs = ub.decode_candidates(refined, jig, soft)
+    got = np.array([m for _, m, _ in msgs], np.uint8).reshape(-1, 7)
+    assert got.tobytes() == golden[name + "/blobs"].tobytes()
+    # the trace of the reference run: the last mode-2 call it made before decoding is one of ours
+    gcalls = golden[name + "/calls"]
+    mode2 = [c for c in gcalls if int(np.frombuffer(c[:4].tobytes(), np.int32)[0]) == 2]
+    for c in mode2:
+        sym = c[52:52 + 162]
+        assert any(np.array_equal(sym, soft[g, t]) for g in range(len(soft)) for t in range(soft.shape[1]))
+
+
+def test_end_to_end_block_mirrors(golden, golden_windows):
+    """FDR -> sync_and_demodulate as a flowgraph wires them, one window at a time"""
+    fdr = ub.FDR(375, 45000, 256, 0, 200, 10, 1500, 10)
+    sd = ub.sync_and_demodulate(375, 45000, 256, 0, 200, 1500)
+    for name in ["ve3emb_c2", "test_1500", "rec_150613", "mix_whales"]:
+        x = golden_windows[name]
+        cands = fdr.transform(x)
+        msgs = sd.demodulate(x, cands)
+        got = np.array(msgs, np.uint8).reshape(-1, 7)
+        assert got.tobytes() == golden[name + "/blobs"].tobytes()
+
+
+def test_nonlinear_candidates_and_intended_t(golden_windows):
+    """both drift models through the fine stage, including hand-made nonlinear candidates"""
+    x = golden_windows["ve3emb_c2"]
+    ctx = ctx_for()
+    cands = np.zeros(3, ub.CAND_DTYPE)
+    for g, k in enumerate([0, 57, 124]):
+        cands[g]["freq"], cands[g]["sync"], cands[g]["shift"], cands[g]["m_type"] = -0.7324219, 0.5, 256, 1
+        cands[g]["V1"], cands[g]["V2"], cands[g]["p1"], cands[g]["p2"] = ob.slm_trajectory(k)
+    check_fine_against_oracle(ctx, x, cands)
+    ctx2 = ctx_for(nonlinear_intended_t=1)
+    ob.lib().orc_set_nonlinear_intended_t(1)
+    try:
+        check_fine_against_oracle(ctx2, x, cands)
+    finally:
+        ob.lib().orc_set_nonlinear_intended_t(0)
+
+
+def test_edges_shift_off_both_ends():
+    """lags that run off the start and the end of the buffer (n <= 0 and n >= 45000 are skipped)"""
+    x, _ = td.synth_window(21, 0, snr_db=-12.0, start=375)
+    ctx = ctx_for(maxdrift=4)
+    cands = np.zeros(4, ub.CAND_DTYPE)
+    for g, (sh, dr) in enumerate([(-300, 0.0), (0, 1.0), (3200, -2.0), (3700, 3.0)]):
+        cands[g]["freq"], cands[g]["sync"], cands[g]["shift"], cands[g]["m_type"], cands[g]["lin_drift"] = 1.4648438, 0.3, sh, 0, dr
+    check_fine_against_oracle(ctx, x, cands)
+
+
+def test_batch_matches_per_window_oracle():
+    """32 seeded synthetic windows, maxdrift 4, SNR -30..0 dB, one submission"""
+    nwin = 32
+    xs, metas = td.synth_batch(nwin, stream=2)
+    ctx = ctx_for(maxdrift=4)
+    ctx.set_debug(True)
+    npk, cands, refined, jig, soft = ctx.coarse_fine(xs)
+    of = ob.OracleFDR(maxdrift=4)
+    base = np.concatenate([[0], np.cumsum(npk)])
+    decoded = 0
+    for w in range(nwin):
+        want, *_ = oracle_on_gpu_ps(of, ctx, xs[w], w)
+        got = cands[base[w]:base[w + 1]]
+        assert cands_equal_exact(got, want)
+        o_ref, o_jigs = ob.demodulate_full(xs[w], want)
+        for j in range(len(want)):
+            g = base[w] + j
+            assert refined["f1"][g].tobytes() == o_ref[j, 0].tobytes() and refined["shift1"][g] == int(o_ref[j, 1])
+            assert refined["sync1"][g].tobytes() == o_ref[j, 3].tobytes()
+            for t, call in enumerate(o_jigs[j]):
+                assert np.array_equal(soft[g, t], np.frombuffer(bytes(call.symbols), np.uint8))
+        msgs = ub.decode_candidates(refined[base[w]:base[w + 1]], jig[base[w]:base[w + 1]], soft[base[w]:base[w + 1]])
+        oblobs, _, _ = ob.demodulate(xs[w], want)
+        assert np.array([m for _, m, _ in msgs], np.uint8).reshape(-1, 7).tobytes() == oblobs.tobytes()
+        decoded += any(np.array_equal(m, metas[w]["msg"]) for _, m, _ in msgs)
+    assert decoded >= nwin // 2  # most of U(-30, 0) dB decodes
+
+
+def test_chunking_overlap_and_device_pointer():
+    """results do not depend on chunk size, on window overlap (stride < fl) or on where samples live"""
+    import torch
+    nwin, stride = 9, 22500
+    stream = np.concatenate([td.synth_window(4, w, snr_db=-14.0)[0][:stride] for w in range(nwin + 1)])
+    windows = np.stack([stream[w * stride:w * stride + 45000] for w in range(nwin)])
+    big = ctx_for(max_windows=64)
+    a = big.coarse_fine(windows)
+    b = big.coarse_fine(stream, nwin=nwin, stride=stride)
+    small = ub.Context(max_windows=16, max_candidates=64)
+    small.info.max_windows  # noqa: B018
+    t = torch.from_numpy(stream.view(np.float32)).cuda()
+    c = big.coarse_fine((t.data_ptr(), stream.size), nwin=nwin, stride=stride)
+    for r in (b, c):
+        for u, v in zip(a, r):
+            assert u.tobytes() == v.tobytes()
+    # chunk size 2048 is fixed inside the library; force several chunks with a tiny context
+    tiny = ub.Context(max_windows=4096, max_candidates=8192)
+    many = np.concatenate([windows] * 300)[:2050]
+    npk, cands, refined, jig, soft = tiny.coarse_fine(many)
+    assert npk.sum() == len(cands)
+    k = int(a[0].sum())
+    assert cands[:k].tobytes() == a[1].tobytes() and soft[:k].tobytes() == a[4].tobytes()
+    assert np.array_equal(npk[:nwin], npk[nwin:2 * nwin]) and np.array_equal(npk[2043:2050], npk[0:7])
+    tiny.close()
+    small.close()
+
+
+def test_empty_noise_and_zero_windows():
+    ctx = ctx_for()
+    z = np.zeros((2, 45000), np.complex64)
+    npk, cands = ctx.coarse(z)
+    of = ob.OracleFDR()
+    assert list(npk) == [len(of.transform(z[0]))] * 2
+    n, _ = td.synth_window(8, 0, snr_db=-80.0)
+    npk, cands, refined, jig, soft = ctx.coarse_fine(n.reshape(1, -1))
+    assert npk[0] == len(of.transform(n))
+    assert ctx.coarse_fine(np.zeros((0, 45000), np.complex64), nwin=0, fetch=False) == 0
+
+
+def test_wide_band_many_candidates():
+    """halfbandwidth 100: 274 pass-band bins, several signals, two-digit candidate counts"""
+    x = sum(td.synth_window(9, w, snr_db=-10.0 - w, f0=f0)[0] for w, f0 in enumerate([-80.0, -33.0, 4.0, 41.0, 77.0]))
+    ctx = ub.Context(halfbandwidth=100, maxdrift=1, max_windows=2)
+    ctx.set_debug(True)
+    npk, cands = ctx.coarse(np.stack([x, x[::-1].copy()]))
+    of = ob.OracleFDR(halfbandwidth=100, maxdrift=1)
+    want, *_ = oracle_on_gpu_ps(of, ctx, x, 0)
+    assert npk[0] == len(want) >= 5
+    assert cands_equal_exact(cands[:npk[0]], want)
+    check_fine_against_oracle(ctx, x, want[:6])
+    ctx.close()
+
+
+def test_errors_are_statuses_not_exits():
+    with pytest.raises(ub.UwsprError) as e:
+        ub.Context(halfbandwidth=188)          # the reference exits (FDR_impl.cc:85-90)
+    assert e.value.status == 1
+    with pytest.raises(ub.UwsprError):
+        ub.Context(halfbandwidth=187)          # the reference reads out of bounds
+    with pytest.raises(ub.UwsprError):
+        ub.Context(spb=128)
+    ctx = ub.Context(max_windows=4, max_candidates=1, halfbandwidth=40)
+    a = td.synth_window(3, 0, snr_db=-12.0, f0=-20.0)[0] + td.synth_window(3, 1, snr_db=-15.0, f0=17.0)[0]
+    with pytest.raises(ub.UwsprError) as e:
+        ctx.coarse(a.reshape(1, -1))
+    assert e.value.status == 3                  # capacity
+    with pytest.raises(ub.UwsprError):
+        ctx.coarse(np.zeros((5, 45000), np.complex64))  # nwin > max_windows
+    ctx.close()
