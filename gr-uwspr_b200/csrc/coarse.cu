@@ -228,10 +228,15 @@ size_t uw_coarse_smem_bytes(const UwDims &d)
     return (size_t)coarse_layout(d.n_rows, d.tile_w, d.n_unique, d.n_hyp).total;
 }
 
+// The attribute is per function, not per context: it is raised to the device's opt-in
+// maximum once, so contexts with different table sizes never lower each other's limit.
 int uw_coarse_setup(const UwDims &d)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)uw_coarse_smem_bytes(d));
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
+    if ((size_t)optin < uw_coarse_smem_bytes(d)) return 1;
+    cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     return e == cudaSuccess ? 0 : 1;
 }
 
