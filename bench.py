@@ -151,9 +151,9 @@ class ClockSampler:
         self.gpu, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -161,21 +161,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """median SM clock and the throttle reasons seen between wall-clock times t0 and t1
+        (the timed region); samples are stamped when read from nvidia-smi's 50 ms loop"""
         if self.proc:
             self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 8 and (t0 is None or t0 - 0.05 <= t <= t1 + 0.05)]
+        if not rows:
+            rows = [r for t, r in self.rows if len(r) >= 8]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None  # noqa: E731
+        sm = sorted(v for v in (num(r[1]) for r in rows) if v is not None)
+        mx = [v for v in (num(r[2]) for r in rows) if v is not None]
+        pw = [v for v in (num(r[3]) for r in rows) if v is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    power_w_max=max(pw) if pw else None, reasons=sorted(reasons), samples=len(sm))
 
 
 def measured_peaks():
@@ -233,6 +239,9 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     xs_dev, truth = gen_windows_torch(nwin, seed=rank, device=dev)
     dptr = (xs_dev.data_ptr(), nwin * FL)
     # pinned host copy for the end-to-end arm
@@ -276,19 +285,18 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_dev()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     stage_ms[:] = 0
     l0 = ctx.launch_count()
+    t_w0 = time.time()
     ms = timed(step_dev, args.steps)
+    t_w1 = time.time()
     launches = ctx.launch_count() - l0
     st = stage_ms / args.steps
-    clocks = sampler.stop() if rank == 0 else None
     ncand = totals[-1]
     for _ in range(min(args.warmup, 1) or 1):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
     npk, cands, refined, jig, soft = e2e_out["r"]
     h2d = nwin * FL * 8
     d2h = npk.nbytes + cands.nbytes + refined.nbytes + jig.nbytes + soft.nbytes
