@@ -236,7 +236,10 @@ int uw_coarse_setup(const UwDims &d)
     if (cudaGetDevice(&dev) != cudaSuccess) return 1;
     if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 1;
     if ((size_t)optin < uw_coarse_smem_bytes(d)) return 1;
-    cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_coarse) != cudaSuccess) return 1;
+    cudaError_t e = cudaFuncSetAttribute(k_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         optin - (int)fa.sharedSizeBytes);
     return e == cudaSuccess ? 0 : 1;
 }
 
