@@ -37,7 +37,17 @@ def ctx_for(maxdrift=0, halfbandwidth=10, threshold=10, max_windows=64, **kw):
 
 
 def cands_equal_exact(a, b):
-    return len(a) == len(b) and td.canon_cands(a).tobytes() == td.canon_cands(b).tobytes()
+    """every field identical; snr alone is compared to 4 ulp: it is 10*log10f(x), and libm's
+    log10f is not correctly rounded (the value depends on the glibc version of the host the
+    reference runs on), while the CUDA path rounds a double-precision log10"""
+    if len(a) != len(b):
+        return False
+    ca, cb = td.canon_cands(a), td.canon_cands(b)
+    if not np.allclose(ca["snr"], cb["snr"], rtol=5e-7, atol=1e-6):
+        return False
+    ca["snr"] = 0
+    cb["snr"] = 0
+    return ca.tobytes() == cb.tobytes()
 
 
 def oracle_on_gpu_ps(of, ctx, x, win=0):
