@@ -38,7 +38,7 @@ struct Buffers {
     uwspr_b200_refined_t *refined = nullptr;
     uwspr_b200_jiggle_t *jig = nullptr;
     uint8_t *soft = nullptr;
-    int *counters = nullptr;  // [0] running total, [1] overflow, [2] ticket coarse, [3] ticket fine, [4] chunk lo
+    int *counters = nullptr;  // [0] running total, [1] overflow; set s at 4+4s: ticket coarse, ticket fine, end of chunk
     // tables
     float *window = nullptr;
     float2 *twiddle = nullptr;
@@ -55,9 +55,11 @@ struct uwspr_b200_ctx {
     int device = 0, sm_count = 0;
     int chunk_windows = 0, max_windows = 0, max_candidates = 0;
     int grid_coarse = 0, grid_fine = 0;
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, compute2 = nullptr, copy = nullptr;
     bool own_compute = true;
-    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr };
+    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[2] = { nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int last_cw = 0;
     std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     float ms[4] = { 0, 0, 0, 0 };
@@ -247,7 +249,12 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         ctx->last_nwin = 0;
         return UWSPR_B200_OK;
     }
-    const int cw = ctx->chunk_windows;
+    // Device-resident input: one stream, chunks as large as the buffers allow (no tails between
+    // chunks).  Host input: chunks of <= 1024 windows alternate between two buffer sets and two
+    // compute streams, so the H2D copy of chunk c+1 and the tail of chunk c-1's kernels overlap
+    // the kernels of chunk c.
+    const bool host = space == UWSPR_B200_HOST;
+    const int cw = host ? std::max(1, std::min(1024, ctx->chunk_windows / 2)) : ctx->chunk_windows;
     const int nchunks = (nwin + cw - 1) / cw;
     if (nchunks > kMaxChunks) return fail(ctx, UWSPR_B200_E_PARAM, "too many chunks: raise max_windows");
     while ((int)ctx->ev.size() < 4 * nchunks) {
@@ -255,8 +262,9 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         CU(cudaEventCreate(&e));
         ctx->ev.push_back(e);
     }
+    cudaStream_t streams[2] = { cs, host && nchunks > 1 ? ctx->compute2 : cs };
     CU(cudaEventRecord(ctx->ev_begin, cs));
-    CU(cudaMemsetAsync(b.counters, 0, 8 * sizeof(int), cs));
+    CU(cudaMemsetAsync(b.counters, 0, 16 * sizeof(int), cs));
     if (!do_coarse) {
         // candidate list comes from the caller (or stays from the previous coarse call)
         if (cands_in) {
@@ -269,53 +277,72 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
             return fail(ctx, UWSPR_B200_E_STATE, "no candidate list on the device for these windows");
         }
     }
+    if (streams[1] != cs) {
+        CU(cudaEventRecord(ctx->ev_fork, cs));
+        CU(cudaStreamWaitEvent(streams[1], ctx->ev_fork, 0));
+    }
     const size_t span_max = (size_t)(cw - 1) * (size_t)win_stride + (size_t)d.fl;
-    if (space == UWSPR_B200_HOST) {
+    if (host) {
         rc = ensure_stage(ctx, span_max);
         if (rc) return rc;
     }
     for (int c = 0; c < nchunks; c++) {
         const int w0 = c * cw, nw = std::min(cw, nwin - w0);
+        const int s = host ? (c & 1) : 0;
+        cudaStream_t st = streams[s];
         const float2 *xdev;
-        if (space == UWSPR_B200_HOST) {
-            // copy stream: wait until the compute of chunk c-2 released this buffer, then copy
-            const int s = c & 1;
+        if (host) {
+            // copy stream: wait until the kernels of chunk c-2 released this buffer set, then copy
             if (c >= 2) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
             const size_t span = (size_t)(nw - 1) * (size_t)win_stride + (size_t)d.fl;
             CU(cudaMemcpyAsync(b.x_stage[s], samples + 2 * (size_t)w0 * (size_t)win_stride, span * sizeof(float2),
                                cudaMemcpyHostToDevice, ctx->copy));
             CU(cudaEventRecord(ctx->ev_h2d[s], ctx->copy));
-            CU(cudaStreamWaitEvent(cs, ctx->ev_h2d[s], 0));
+            CU(cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0));
             xdev = b.x_stage[s];
         } else {
             xdev = reinterpret_cast<const float2 *>(samples) + (size_t)w0 * (size_t)win_stride;
         }
+        // per-set slices of the chunk buffers
+        const size_t so = (size_t)s * cw;
+        float *amp = b.amp + so * d.n_rows * d.nbp;
+        float *psd = (ctx->debug_ps && b.ps_dbg) ? b.ps_dbg + so * d.n_rows * d.nbp : nullptr;
+        float *psavg = b.psavg + so * d.nbp;
+        UwPeak *peaks = b.peaks + so * d.maxcand;
+        int *set = b.counters + 4 + 4 * s;
         cudaEvent_t *e = &ctx->ev[4 * c];
-        CU(cudaEventRecord(e[0], cs));
+        CU(cudaEventRecord(e[0], st));
         if (do_coarse) {
-            uw_launch_spectrogram(d, xdev, (long long)win_stride, nw, b.window, b.twiddle, b.amp,
-                                  ctx->debug_ps ? b.ps_dbg : nullptr, b.psavg, b.peaks, b.npk + w0, cs);
+            uw_launch_spectrogram(d, xdev, (long long)win_stride, nw, b.window, b.twiddle, amp, psd, psavg, peaks,
+                                  b.npk + w0, st);
             ctx->launches++;
         }
-        CU(cudaEventRecord(e[1], cs));
-        // work list of this chunk: items [counters[4], counters[0])
-        uw_launch_worklist(b.npk + w0, nw, ctx->max_candidates, b.base + w0, b.items, b.counters, cs);
+        CU(cudaEventRecord(e[1], st));
+        // the running total makes the work lists of consecutive chunks sequential
+        if (c >= 1 && streams[1] != cs) CU(cudaStreamWaitEvent(st, ctx->ev_wl[s ^ 1], 0));
+        uw_launch_worklist(b.npk + w0, nw, ctx->max_candidates, b.base + w0, b.items, b.counters, set, st);
         ctx->launches++;
+        if (streams[1] != cs) CU(cudaEventRecord(ctx->ev_wl[s], st));
         if (do_coarse) {
-            uw_launch_coarse(d, b.amp, b.peaks, b.items, b.counters, ctx->max_candidates, b.off4, b.hyp_unique,
-                             b.cands, b.counters + 2, ctx->grid_coarse, cs);
+            uw_launch_coarse(d, amp, peaks, b.items, set + 2, ctx->max_candidates, b.off4, b.hyp_unique, b.cands, set,
+                             ctx->grid_coarse, st);
             ctx->launches++;
         }
-        CU(cudaEventRecord(e[2], cs));
+        CU(cudaEventRecord(e[2], st));
         if (do_fine) {
-            uw_launch_fine(d, xdev, (long long)win_stride, b.items, b.counters, ctx->max_candidates, b.cands, jig_first,
-                           jig_count, b.refined, b.jig, b.soft, b.counters + 3, ctx->grid_fine, cs);
+            uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 2, ctx->max_candidates, b.cands, jig_first,
+                           jig_count, b.refined, b.jig, b.soft, set + 1, ctx->grid_fine, st);
             ctx->launches++;
         }
-        CU(cudaEventRecord(e[3], cs));
-        if (space == UWSPR_B200_HOST) CU(cudaEventRecord(ctx->ev_free[c & 1], cs));
+        CU(cudaEventRecord(e[3], st));
+        if (host) CU(cudaEventRecord(ctx->ev_free[s], st));
     }
-    int h_counters[8];
+    if (streams[1] != cs) {
+        CU(cudaEventRecord(ctx->ev_join, streams[1]));
+        CU(cudaStreamWaitEvent(cs, ctx->ev_join, 0));
+    }
+    ctx->last_cw = cw;
+    int h_counters[4];
     CU(cudaMemcpyAsync(h_counters, b.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, cs));
     CU(cudaStreamSynchronize(cs));
     CU(cudaGetLastError());
@@ -426,7 +453,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     ctx->sm_count = prop.multiProcessorCount;
     UwDims &d = ctx->d;
     ctx->max_windows = p.max_windows > 0 ? p.max_windows : 1;
-    ctx->chunk_windows = std::min(ctx->max_windows, 2048);
+    ctx->chunk_windows = std::min(ctx->max_windows, 16384);
     const long long def_cap = (long long)ctx->max_windows * d.maxcand;
     ctx->max_candidates = p.max_candidates > 0 ? p.max_candidates : (int)std::min<long long>(def_cap, 1 << 22);
     Buffers &b = ctx->b;
@@ -439,8 +466,8 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaMalloc(&b.refined, cap * sizeof(uwspr_b200_refined_t)));
     CUC(cudaMalloc(&b.jig, cap * UWSPR_B200_NJIG * sizeof(uwspr_b200_jiggle_t)));
     CUC(cudaMalloc(&b.soft, cap * UWSPR_B200_NJIG * UW_NSYM));
-    CUC(cudaMalloc(&b.counters, 8 * sizeof(int)));
-    CUC(cudaMemset(b.counters, 0, 8 * sizeof(int)));
+    CUC(cudaMalloc(&b.counters, 16 * sizeof(int)));
+    CUC(cudaMemset(b.counters, 0, 16 * sizeof(int)));
     // tables
     std::vector<float> window(UW_FFT_N);
     for (int i = 0; i < d.size; i++) window[i] = (float)sin((M_PI / (d.size - 1)) * i);  // FDR_impl.cc:103-105
@@ -459,9 +486,13 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaMemcpy(b.hyp_unique, hyp_unique.data(), hyp_unique.size() * sizeof(short), cudaMemcpyHostToDevice));
     CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     for (int q = 0; q < 2; q++) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_h2d[q], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&ctx->ev_free[q], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ctx->ev_wl[q], cudaEventDisableTiming));
     }
     CUC(cudaEventCreate(&ctx->ev_begin));
     CUC(cudaEventCreate(&ctx->ev_end));
@@ -488,11 +519,15 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     for (int q = 0; q < 2; q++) {
         if (ctx->ev_h2d[q]) cudaEventDestroy(ctx->ev_h2d[q]);
         if (ctx->ev_free[q]) cudaEventDestroy(ctx->ev_free[q]);
+        if (ctx->ev_wl[q]) cudaEventDestroy(ctx->ev_wl[q]);
     }
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->compute && ctx->own_compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 
@@ -586,7 +621,7 @@ int uwspr_b200_debug_spectrogram(uwspr_b200_ctx *ctx, int win, float *ps, float 
 {
     if (!ctx) return UWSPR_B200_E_PARAM;
     if (!ctx->debug_ps || !ctx->b.ps_dbg) return fail(ctx, UWSPR_B200_E_STATE, "enable uwspr_b200_set_debug first");
-    if (win < 0 || win >= ctx->last_nwin || win >= ctx->chunk_windows)
+    if (win < 0 || win >= ctx->last_nwin || ctx->last_nwin > ctx->last_cw)
         return fail(ctx, UWSPR_B200_E_PARAM, "window not in the last (single-chunk) call");
     CU(cudaSetDevice(ctx->device));
     const UwDims &d = ctx->d;

@@ -55,7 +55,7 @@ void uw_launch_spectrogram(const UwDims &d, const float2 *x, long long win_strid
                            const float *window, const float2 *twiddle, float *amp, float *ps_dbg,
                            float *psavg, UwPeak *peaks, int *npk, cudaStream_t s);
 void uw_launch_worklist(const int *npk, int nwin, int cap, int *base, UwItem *items, int *counters,
-                        cudaStream_t s);
+                        int *set, cudaStream_t s);
 void uw_launch_coarse(const UwDims &d, const float *amp, const UwPeak *peaks, const UwItem *items,
                       const int *total, int cap, const uint32_t *off4, const short *hyp_unique,
                       uwspr_b200_candidate_t *cands, int *ticket, int grid, cudaStream_t s);

@@ -234,12 +234,13 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
 
 // Exclusive scan of npk over the windows of one chunk + expansion into the compact work
 // list.  counters: [0] running total over the chunks of this call (in/out), [1] overflow
-// flag, [2] coarse ticket, [3] fine ticket, [4] first item of this chunk.  Item indices are
+// flag; set: the chunk's own {coarse ticket, fine ticket, end of its items} (chunks in
+// flight on different streams use different sets).  Item indices are
 // global to the call (so results land compactly, window-major); item.win is relative to
 // the chunk.
 __global__ void __launch_bounds__(1024)
 k_worklist(const int *__restrict__ npk, int nwin, int cap, int *__restrict__ base,
-           UwItem *__restrict__ items, int *__restrict__ counters)
+           UwItem *__restrict__ items, int *__restrict__ counters, int *__restrict__ set)
 {
     __shared__ int part[1024];
     const int tid = threadIdx.x;
@@ -272,9 +273,9 @@ k_worklist(const int *__restrict__ npk, int nwin, int cap, int *__restrict__ bas
         const int end = run0 + part[1023];
         counters[0] = end;
         if (end > cap) counters[1] = 1;
-        counters[2] = run0;
-        counters[3] = run0;
-        counters[4] = run0;
+        set[0] = run0;  // coarse ticket
+        set[1] = run0;  // fine ticket
+        set[2] = min(end, cap);  // end of this chunk's items
     }
 }
 
@@ -290,7 +291,7 @@ void uw_launch_spectrogram(const UwDims &d, const float2 *x, long long win_strid
 }
 
 void uw_launch_worklist(const int *npk, int nwin, int cap, int *base, UwItem *items, int *counters,
-                        cudaStream_t s)
+                        int *set, cudaStream_t s)
 {
-    k_worklist<<<1, 1024, 0, s>>>(npk, nwin, cap, base, items, counters);
+    k_worklist<<<1, 1024, 0, s>>>(npk, nwin, cap, base, items, counters, set);
 }
