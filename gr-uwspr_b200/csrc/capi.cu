@@ -60,6 +60,7 @@ struct uwspr_b200_ctx {
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[2] = { nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int last_cw = 0;
+    bool last_host = false;
     std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     float ms[4] = { 0, 0, 0, 0 };
@@ -342,6 +343,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         CU(cudaStreamWaitEvent(cs, ctx->ev_join, 0));
     }
     ctx->last_cw = cw;
+    ctx->last_host = host;
     int h_counters[4];
     CU(cudaMemcpyAsync(h_counters, b.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, cs));
     CU(cudaStreamSynchronize(cs));
@@ -621,17 +623,22 @@ int uwspr_b200_debug_spectrogram(uwspr_b200_ctx *ctx, int win, float *ps, float 
 {
     if (!ctx) return UWSPR_B200_E_PARAM;
     if (!ctx->debug_ps || !ctx->b.ps_dbg) return fail(ctx, UWSPR_B200_E_STATE, "enable uwspr_b200_set_debug first");
-    if (win < 0 || win >= ctx->last_nwin || ctx->last_nwin > ctx->last_cw)
-        return fail(ctx, UWSPR_B200_E_PARAM, "window not in the last (single-chunk) call");
+    // the chunk buffers keep the last chunk (device input) or the last two (host input, two sets)
+    const int cw = ctx->last_cw > 0 ? ctx->last_cw : 1;
+    const int nchunks = (ctx->last_nwin + cw - 1) / cw;
+    const int chunk = win / cw;
+    if (win < 0 || win >= ctx->last_nwin || chunk < nchunks - (ctx->last_host ? 2 : 1))
+        return fail(ctx, UWSPR_B200_E_PARAM, "window is not in the chunks still held on the device");
+    const size_t slot = (size_t)(ctx->last_host ? (chunk & 1) : 0) * cw + (size_t)(win - chunk * cw);
     CU(cudaSetDevice(ctx->device));
     const UwDims &d = ctx->d;
     std::vector<float> tmp((size_t)d.n_rows * d.nbp);
     if (ps) {
-        CU(cudaMemcpy(tmp.data(), ctx->b.ps_dbg + (size_t)win * d.n_rows * d.nbp, tmp.size() * sizeof(float),
+        CU(cudaMemcpy(tmp.data(), ctx->b.ps_dbg + slot * d.n_rows * d.nbp, tmp.size() * sizeof(float),
                       cudaMemcpyDeviceToHost));
         for (int r = 0; r < d.n_rows; r++) memcpy(ps + (size_t)r * d.n_bins, &tmp[(size_t)r * d.nbp], sizeof(float) * d.n_bins);
     }
-    if (psavg) CU(cudaMemcpy(psavg, ctx->b.psavg + (size_t)win * d.nbp, sizeof(float) * d.n_bins, cudaMemcpyDeviceToHost));
+    if (psavg) CU(cudaMemcpy(psavg, ctx->b.psavg + slot * d.nbp, sizeof(float) * d.n_bins, cudaMemcpyDeviceToHost));
     return UWSPR_B200_OK;
 }
 
