@@ -55,9 +55,13 @@ __device__ __forceinline__ void fft8(float2 *v)
     v[7] = csub(b6, b7);
 }
 
+// one pad slot every 8 entries: the stride-8 stores of the Stockham passes become stride 9
+#define PADX(i) ((i) + ((i) >> 3))
+
 struct __align__(16) SpecSmem {
-    float2 buf[kGroups][UW_FFT_N];   // inter-pass exchange, one FFT per group
-    float2 tw[UW_FFT_N];             // exp(-2 pi i t / 512)
+    float2 buf[kGroups][UW_FFT_N + UW_FFT_N / 8];  // inter-pass exchange, one FFT per group, padded (PADX)
+    float2 tw1[8][8];                // pass-1 twiddles exp(-2 pi i 8 r k / 512), [r][k]
+    float2 tw2[8][64];               // pass-2 twiddles exp(-2 pi i r j / 512), [r][j]
     float psrow[kGroups][UW_FFT_N];  // powers of the kept bins of the four rows of this iteration
     float psavg[UW_FFT_N];           // column sums of the kept bins
     float smspec[UW_FFT_N];          // smoothed / normalised spectrum, finpb entries
@@ -81,7 +85,9 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     if (win >= nwin) return;
     const float2 *xw = x + (long long)win * win_stride;
 
-    for (int t = tid; t < UW_FFT_N; t += kThreads) sm.tw[t] = twiddle[t];
+    // twiddles laid out so that the lanes of a warp read consecutive words (no bank conflicts)
+    for (int t = tid; t < 64; t += kThreads) sm.tw1[t >> 3][t & 7] = twiddle[(8 * (t >> 3) * (t & 7)) & (UW_FFT_N - 1)];
+    for (int t = tid; t < 512; t += kThreads) sm.tw2[t >> 6][t & 63] = twiddle[((t >> 6) * (t & 63)) & (UW_FFT_N - 1)];
     float wj[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) wj[r] = window[j + 64 * r];
@@ -92,22 +98,33 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     __syncthreads();
 
     const int n_iter = (d.n_rows + kGroups - 1) / kGroups;
+    // samples of the next iteration are fetched while the current FFT runs
+    float2 nx[8];
+    {
+        const bool l0 = g < d.n_rows;
+        const float2 *src = xw + (long long)g * UW_HOP + j;
+#pragma unroll
+        for (int r = 0; r < 8; r++) nx[r] = l0 ? __ldg(src + 64 * r) : make_float2(0.f, 0.f);
+    }
     for (int it = 0; it < n_iter; it++) {
         const int row = it * kGroups + g;
         const bool live = row < d.n_rows;
         float2 v[8];
         if (live) {
-            const float2 *src = xw + (long long)row * UW_HOP + j;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 s = __ldg(src + 64 * r);
                 // FDR_impl.cc:230-231: the fp32 sample times the fp32 window, rounded once
-                v[r] = make_float2(__fmul_rn(s.x, wj[r]), __fmul_rn(s.y, wj[r]));
+                v[r] = make_float2(__fmul_rn(nx[r].x, wj[r]), __fmul_rn(nx[r].y, wj[r]));
+            }
+            if (row + kGroups < d.n_rows) {
+                const float2 *src = xw + (long long)(row + kGroups) * UW_HOP + j;
+#pragma unroll
+                for (int r = 0; r < 8; r++) nx[r] = __ldg(src + 64 * r);
             }
             // pass 0 (Ns = 1): no twiddles; out[8j + r] = X[r]
             fft8(v);
 #pragma unroll
-            for (int r = 0; r < 8; r++) sm.buf[g][8 * j + r] = v[r];
+            for (int r = 0; r < 8; r++) sm.buf[g][PADX(8 * j + r)] = v[r];
         }
         __syncthreads();
         if (live) {
@@ -115,8 +132,8 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             const int k = j & 7;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 s = sm.buf[g][j + 64 * r];
-                v[r] = (r == 0) ? s : cmul(s, sm.tw[8 * r * k]);
+                float2 s = sm.buf[g][PADX(j + 64 * r)];
+                v[r] = (r == 0) ? s : cmul(s, sm.tw1[r][k]);
             }
             fft8(v);
         }
@@ -124,15 +141,15 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
         if (live) {
             const int j0 = (j >> 3) * 64 + (j & 7);
 #pragma unroll
-            for (int r = 0; r < 8; r++) sm.buf[g][j0 + 8 * r] = v[r];
+            for (int r = 0; r < 8; r++) sm.buf[g][PADX(j0 + 8 * r)] = v[r];
         }
         __syncthreads();
         if (live) {
             // pass 2 (Ns = 64): thread j ends with X[j + 64 r]
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 s = sm.buf[g][j + 64 * r];
-                v[r] = (r == 0) ? s : cmul(s, sm.tw[r * j]);
+                float2 s = sm.buf[g][PADX(j + 64 * r)];
+                v[r] = (r == 0) ? s : cmul(s, sm.tw2[r][j]);
             }
             fft8(v);
             float *amp_row = amp + ((long long)win * d.n_rows + row) * d.nbp;
