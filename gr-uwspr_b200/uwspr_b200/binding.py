@@ -15,6 +15,8 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_deinterleave", "uwspr_b200_fano", "uwspr_b200_decode_candidate", "uwspr_b200_host_alloc",
     "uwspr_b200_host_free", "uwspr_b200_set_stream", "uwspr_b200_set_debug", "uwspr_b200_debug_spectrogram",
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
+    "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
+    "uwspr_b200_receiver_windows",
 ]
 
 CAND_DTYPE = np.dtype(
@@ -103,6 +105,15 @@ def load_library():
     L.uwspr_b200_last_timing.argtypes = [vp, vp]
     L.uwspr_b200_launch_count.restype = i64
     L.uwspr_b200_launch_count.argtypes = [vp]
+    L.uwspr_b200_receiver_create.restype = C.c_int
+    L.uwspr_b200_receiver_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(vp)]
+    L.uwspr_b200_receiver_destroy.argtypes = [vp]
+    L.uwspr_b200_receiver_push.restype = C.c_int
+    L.uwspr_b200_receiver_push.argtypes = [vp, vp, i64, C.c_int]
+    L.uwspr_b200_receiver_pop.restype = C.c_int
+    L.uwspr_b200_receiver_pop.argtypes = [vp, vp, vp, vp]
+    L.uwspr_b200_receiver_windows.restype = i64
+    L.uwspr_b200_receiver_windows.argtypes = [vp]
     _lib = L
     return L
 
@@ -295,3 +306,44 @@ class sync_and_demodulate:
         npk = np.array([len(cands)], np.int32)
         refined, jig, soft = self.ctx.fine(np.asarray(window).reshape(1, -1), npk, cands)
         return [m for _, m, _ in decode_candidates(refined, jig, soft)]
+
+
+class Receiver:
+    """batched receive chain of one stream: sliding window (shift seconds) -> device -> host decoder"""
+
+    def __init__(self, fs=375, fl=45000, spb=256, maxdrift=0, maxfreqs=200, halfbandwidth=10, cf=1500, threshold=10,
+                 shift=9, batch_windows=16, device=0):
+        self.L = load_library()
+        prm = Params(fs, fl, spb, maxdrift, maxfreqs, halfbandwidth, cf, threshold, device, batch_windows, 0, 0)
+        h = C.c_void_p()
+        st = self.L.uwspr_b200_receiver_create(C.byref(prm), shift, batch_windows, C.byref(h))
+        if st != 0:
+            raise UwsprError(st, self.L.uwspr_b200_create_error().decode() or self.L.uwspr_b200_status_string(st).decode())
+        self.h = h
+
+    def push(self, samples, flush=False):
+        a = np.ascontiguousarray(samples, dtype=np.complex64)
+        st = self.L.uwspr_b200_receiver_push(self.h, _p(a), a.size, int(flush))
+        if st != 0:
+            raise UwsprError(st, self.L.uwspr_b200_status_string(st).decode())
+        out = []
+        msg = np.zeros(7, np.int8)
+        win = C.c_int64()
+        cand = np.zeros(1, CAND_DTYPE)
+        while self.L.uwspr_b200_receiver_pop(self.h, _p(msg), C.byref(win), _p(cand)):
+            out.append((win.value, msg.view(np.uint8).copy(), cand[0].copy()))
+        return out
+
+    def windows_done(self):
+        return int(self.L.uwspr_b200_receiver_windows(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.uwspr_b200_receiver_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -179,6 +179,24 @@ UWSPR_B200_API int uwspr_b200_decode_candidate(const uwspr_b200_refined_t *refin
                                                int jig_count, int8_t *message7, int32_t *idt_used,
                                                uint32_t *fano_cycles);
 
+/* ---- batched receive chain of one stream (one hydrophone channel) -----------------------
+ * The sliding window of lib/sliding_window_stream_to_pdu_impl.cc:98-138 (window k =
+ * stream[k*shift*fs, k*shift*fs + fl)) feeding the device `batch_windows` windows per
+ * submission as one contiguous span + stride, then the host-side decode loop.  Messages come
+ * out in (window, candidate) order, one per decoded candidate, no de-duplication -- as the
+ * reference publishes them. */
+typedef struct uwspr_b200_receiver uwspr_b200_receiver;
+UWSPR_B200_API int uwspr_b200_receiver_create(const uwspr_b200_params_t *params, int shift_seconds,
+                                              int batch_windows, uwspr_b200_receiver **out);
+UWSPR_B200_API void uwspr_b200_receiver_destroy(uwspr_b200_receiver *rx);
+/* appends n_complex stream samples (interleaved I,Q); flush != 0 also processes every complete
+ * window still buffered */
+UWSPR_B200_API int uwspr_b200_receiver_push(uwspr_b200_receiver *rx, const float *iq, int64_t n_complex, int flush);
+/* returns 1 and fills the outputs (any may be NULL) while decoded messages are queued */
+UWSPR_B200_API int uwspr_b200_receiver_pop(uwspr_b200_receiver *rx, int8_t *message7, int64_t *window,
+                                           uwspr_b200_candidate_t *cand);
+UWSPR_B200_API int64_t uwspr_b200_receiver_windows(const uwspr_b200_receiver *rx);
+
 /* ---- utilities ------------------------------------------------------------------------- */
 /* pinned host memory for sample / result buffers (cudaHostAlloc / cudaFreeHost) */
 UWSPR_B200_API int uwspr_b200_host_alloc(void **ptr, size_t bytes);

@@ -270,3 +270,37 @@ def test_errors_are_statuses_not_exits():
     with pytest.raises(ub.UwsprError):
         ctx.coarse(np.zeros((5, 45000), np.complex64))  # nwin > max_windows
     ctx.close()
+
+
+def test_batched_receiver_on_sliding_stream():
+    """uwspr_b200_receiver: window k = stream[k*shift*fs, +fl) (sliding_window_stream_to_pdu_impl.cc:113-135),
+    batches of 5 windows per submission; per window the same messages, in the same order, as the
+    reference chain FDR -> sync_and_demodulate produces for that window"""
+    from oracle import testdata as tdd
+    stride, nwin = 9 * 375, 13
+    n = 45000 + (nwin - 1) * stride
+    rng = np.random.default_rng(77)
+    stream = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * np.sqrt(0.15 / 10 ** (-1.2) / 2.0)
+    truth = []
+    for start, f0, seed in ((9000, -4.0, 1), (37000, 3.1, 2)):
+        msg = tdd.message_bytes(np.random.default_rng(seed))
+        sig = tdd.modulate(ob.channel_symbols(msg), f0=f0, drift=0.0, start=0, fl=162 * 256)
+        stream[start:start + 162 * 256] += sig
+        truth.append(bytes(msg))
+    stream = stream.astype(np.complex64)
+    rx = ub.Receiver(maxdrift=0, shift=9, batch_windows=5)
+    got = []
+    for lo in range(0, n, 10000):   # arbitrary push sizes
+        got += rx.push(stream[lo:lo + 10000])
+    got += rx.push(np.zeros(0, np.complex64), flush=True)
+    assert rx.windows_done() == nwin
+    of = ob.OracleFDR(maxdrift=0)
+    want = []
+    for k in range(nwin):
+        x = stream[k * stride:k * stride + 45000]
+        oc = of.transform(x)
+        blobs, _, _ = ob.demodulate(x, oc)
+        want += [(k, bytes(b)) for b in blobs]
+    assert [(w, bytes(m)) for w, m, _ in got] == want
+    assert {m for _, m in want} == set(truth)  # both transmissions are decoded (several times each)
+    rx.close()
