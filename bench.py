@@ -184,6 +184,19 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, reasons=sorted(reasons), samples=len(sm))
 
 
+def recorded_traffic(nwin):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json, written from `ncu --set full` by tools/ncu_summary.py --traffic);
+    only returned when the capture was taken at this workload size"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if int(t.get("windows", -1)) == int(nwin):
+            return float(t["k_fine_dram_bytes"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -299,6 +312,17 @@ def run_ours(args):
     clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
     npk, cands, refined, jig, soft = e2e_out["r"]
     h2d = nwin * FL * 8
+    # context for the end-to-end number: the plain pinned-host -> device copy rate of this box
+    scratch = torch.empty_like(xs_dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch.copy_(xs_host_t, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    ev0.record(stream)
+    scratch.copy_(xs_host_t, non_blocking=True)
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    pcie_gbs = h2d / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del scratch
     d2h = npk.nbytes + cands.nbytes + refined.nbytes + jig.nbytes + soft.nbytes
 
     counts = gather_counts(nwin, dist if world > 1 else None)
@@ -334,11 +358,12 @@ def run_ours(args):
                     windows_per_gpu=nwin, input_bytes_per_gpu=h2d, l2="inputs larger than L2 (3.6 GB vs 126 MB)",
                     jiggles="all 17 per gated candidate", candidates=ncand, gated=gated, sync_evaluations=evals,
                     **{k: PARAMS[k] for k in ("maxdrift", "halfbandwidth", "threshold", "maxfreqs")}),
-        e2e=dict(value=e2e_value, unit="windows/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(d2h), ms_per_step=ms_e2e / args.steps),
+        e2e=dict(value=e2e_value, unit="windows/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(d2h), ms_per_step=ms_e2e / args.steps,
+                 pcie_h2d_gbs=pcie_gbs, pcie_bound_windows_per_s=world * pcie_gbs * 1e9 / (FL * 8)),
         gpu_launches=int(launches),
         stage_ms=dict(spectrogram_normalizer=float(st[0]), coarse_search=float(st[1]), fine_sync_demod=fine_ms, call=float(st[3])),
         roofline=dict(bound="hbm", kernel="k_fine (fine sync + soft symbols)", achieved=alg_bytes / (fine_ms * 1e-3) / 1e9, peak=hbm_peak,
-                      unit="GB/s", frac=alg_bytes / (fine_ms * 1e-3) / 1e9 / hbm_peak, traffic=None,
+                      unit="GB/s", frac=alg_bytes / (fine_ms * 1e-3) / 1e9 / hbm_peak, traffic=recorded_traffic(nwin),
                       peak_source="MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650 GB/s",
                       note="the path is FP32-pipe bound, not HBM bound: see roofline_fp32"),
         roofline_fp32=dict(bound="fp32", achieved=alg_flops / (ms / args.steps * 1e-3) / 1e12, peak=74.4, unit="TFLOP/s",

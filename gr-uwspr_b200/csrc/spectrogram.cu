@@ -71,7 +71,7 @@ struct __align__(16) SpecSmem {
     UwPeak sorted[256];
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int nwin,
               const float *__restrict__ window, const float2 *__restrict__ twiddle,
               float *__restrict__ amp, float *__restrict__ ps_dbg, float *__restrict__ psavg_out,
@@ -95,6 +95,13 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     // this thread owns the column sums of kept bins tid and tid+256
     float acc0 = 0.0f, acc1 = 0.0f;
     const int nb = d.n_bins;
+    // which of this thread's eight pass-2 outputs X[j + 64 r] fall in the kept bins
+    unsigned keep = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int c = ((j + 64 * r + UW_FFT_N / 2) & (UW_FFT_N - 1)) - d.bin_lo;
+        if (c >= 0 && c < nb) keep |= 1u << r;
+    }
     __syncthreads();
 
     const int n_iter = (d.n_rows + kGroups - 1) / kGroups;
@@ -144,14 +151,27 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             for (int r = 0; r < 8; r++) sm.buf[g][PADX(j0 + 8 * r)] = v[r];
         }
         __syncthreads();
-        if (live) {
-            // pass 2 (Ns = 64): thread j ends with X[j + 64 r]
+        if (live && keep) {
+            // pass 2 (Ns = 64): thread j ends with X[j + 64 r].  Narrow pass bands keep one output
+            // per thread at most (X[j] below DC+, X[j+448] above): those are summed directly
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 float2 s = sm.buf[g][PADX(j + 64 * r)];
                 v[r] = (r == 0) ? s : cmul(s, sm.tw2[r][j]);
             }
-            fft8(v);
+            if (keep == 0x01u) {
+                v[0] = cadd(cadd(cadd(v[0], v[4]), cadd(v[2], v[6])), cadd(cadd(v[1], v[5]), cadd(v[3], v[7])));
+            } else if (keep == 0x80u) {
+                // X[7] = d0 + d1 e^{i pi/4} + i d2 + d3 e^{3 i pi/4},  dn = v[n] - v[n+4]
+                const float h = 0.70710678118654752440f;
+                const float2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+                const float2 e1 = make_float2((d1.x - d1.y) * h, (d1.x + d1.y) * h);
+                const float2 e2 = make_float2(-d2.y, d2.x);
+                const float2 e3 = make_float2(-(d3.x + d3.y) * h, (d3.x - d3.y) * h);
+                v[7] = cadd(cadd(d0, e2), cadd(e1, e3));
+            } else {
+                fft8(v);
+            }
             float *amp_row = amp + ((long long)win * d.n_rows + row) * d.nbp;
             float *dbg_row = ps_dbg ? ps_dbg + ((long long)win * d.n_rows + row) * d.nbp : nullptr;
 #pragma unroll
