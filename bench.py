@@ -293,8 +293,10 @@ def run_ours(args):
 
     e2e_out = {}
 
+    out_bufs = ctx.result_buffers(nwin)   # pinned, allocated once (as a streaming caller would)
+
     def step_e2e():
-        e2e_out["r"] = ctx.coarse_fine(xs_host, nwin=nwin)
+        e2e_out["r"] = ctx.coarse_fine(xs_host, nwin=nwin, out=out_bufs)
 
     for _ in range(args.warmup):
         step_dev()

@@ -144,6 +144,7 @@ class Context:
             raise UwsprError(st, self.L.uwspr_b200_create_error().decode() or self.L.uwspr_b200_status_string(st).decode())
         self.h = h
         self.fl = fl
+        self._pinned = []
         inf = Info()
         self._check(self.L.uwspr_b200_info(self.h, C.byref(inf)))
         self.info = inf
@@ -154,6 +155,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr in getattr(self, "_pinned", []):
+                self.L.uwspr_b200_host_free(ptr)
+            self._pinned = []
             self.L.uwspr_b200_destroy(self.h)
             self.h = None
 
@@ -210,7 +214,28 @@ class Context:
                                            jig_count, _p(refined), _p(jig), _p(soft)))
         return refined, jig, soft
 
-    def coarse_fine(self, samples, nwin=None, stride=None, jig_first=0, jig_count=NJIG, fetch=True):
+    def result_buffers(self, nwin, jig_count=NJIG, pinned=True):
+        """caller-owned result buffers for coarse_fine(out=...), page-locked so the device->host
+        copies run at link speed (cudaHostAlloc through uwspr_b200_host_alloc)"""
+        cap = self.info.max_candidates
+        spec = [("npk", (nwin,), np.dtype(np.int32)), ("cands", (cap,), CAND_DTYPE), ("refined", (cap,), REFINED_DTYPE),
+                ("jig", (cap, jig_count), JIG_DTYPE), ("soft", (cap, jig_count, NSYM), np.dtype(np.uint8))]
+        out = {}
+        for name, shape, dt in spec:
+            n = int(np.prod(shape)) * dt.itemsize
+            if pinned:
+                ptr = C.c_void_p()
+                st = self.L.uwspr_b200_host_alloc(C.byref(ptr), max(n, 1))
+                if st != 0:
+                    raise UwsprError(st, "cannot allocate pinned host memory")
+                raw = (C.c_ubyte * max(n, 1)).from_address(ptr.value)
+                self._pinned.append(ptr)
+                out[name] = np.frombuffer(raw, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+            else:
+                out[name] = np.zeros(shape, dt)
+        return out
+
+    def coarse_fine(self, samples, nwin=None, stride=None, jig_first=0, jig_count=NJIG, fetch=True, out=None):
         stride = self.fl if stride is None else stride
         ptr, space, keep = _samples_arg(samples)
         nwin = self._nwin(samples, nwin, stride) if not isinstance(samples, tuple) else nwin
@@ -220,6 +245,13 @@ class Context:
             self._check(self.L.uwspr_b200_coarse_fine(self.h, ptr, space, stride, nwin, jig_first, jig_count, None, None,
                                                       0, C.byref(total), None, None, None))
             return total.value
+        if out is not None:
+            # views into the caller's buffers, no copies
+            self._check(self.L.uwspr_b200_coarse_fine(self.h, ptr, space, stride, nwin, jig_first, jig_count,
+                                                      _p(out["npk"]), _p(out["cands"]), cap, C.byref(total),
+                                                      _p(out["refined"]), _p(out["jig"]), _p(out["soft"])))
+            t = total.value
+            return out["npk"][:nwin], out["cands"][:t], out["refined"][:t], out["jig"][:t], out["soft"][:t]
         npk = np.zeros(nwin, np.int32)
         cands = np.zeros(cap, CAND_DTYPE)
         refined = np.zeros(cap, REFINED_DTYPE)
