@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_host_free", "uwspr_b200_set_stream", "uwspr_b200_set_debug", "uwspr_b200_debug_spectrogram",
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
-    "uwspr_b200_receiver_windows",
+    "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack",
 ]
 
 CAND_DTYPE = np.dtype(
@@ -114,6 +114,9 @@ def load_library():
     L.uwspr_b200_receiver_pop.argtypes = [vp, vp, vp, vp]
     L.uwspr_b200_receiver_windows.restype = i64
     L.uwspr_b200_receiver_windows.argtypes = [vp]
+    L.uwspr_b200_hashtab_bytes.restype = C.c_size_t
+    L.uwspr_b200_unpack.restype = C.c_int
+    L.uwspr_b200_unpack.argtypes = [vp, vp, vp, C.c_size_t]
     _lib = L
     return L
 
@@ -379,3 +382,17 @@ class Receiver:
             self.close()
         except Exception:
             pass
+
+
+class WSPR_unpacker:
+    """uwspr.WSPR_unpacker's text (lib/helpers.cc:494-590): unpack(message7) -> (noprint, "CALL GRID dBm")"""
+
+    def __init__(self):
+        self.L = load_library()
+        self.hashtab = np.zeros(self.L.uwspr_b200_hashtab_bytes(), np.uint8)
+
+    def unpack(self, message7):
+        m = np.ascontiguousarray(message7, dtype=np.uint8)
+        text = np.zeros(64, np.uint8)
+        noprint = self.L.uwspr_b200_unpack(_p(m), _p(self.hashtab), _p(text), text.size)
+        return noprint, bytes(text).split(b"\0")[0].decode("latin1")

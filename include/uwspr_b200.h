@@ -179,6 +179,14 @@ UWSPR_B200_API int uwspr_b200_decode_candidate(const uwspr_b200_refined_t *refin
                                                int jig_count, int8_t *message7, int32_t *idt_used,
                                                uint32_t *fano_cycles);
 
+/* ---- WSPR_unpacker's text: lib/helpers.cc:494-590 (unpk_) -------------------------------
+ * message7 -> "CALL GRID dBm" (type 1), "PFX/CALL dBm" (type 2) or "<CALL> GRID6 dBm" (type 3).
+ * hashtab: caller-owned callsign hash table of uwspr_b200_hashtab_bytes() zero-initialised
+ * bytes (the reference keeps one per unpacker block and persists it in hashtable.txt).
+ * Returns the reference's `noprint` flag (0 = print), or -1 on bad arguments. */
+UWSPR_B200_API size_t uwspr_b200_hashtab_bytes(void);
+UWSPR_B200_API int uwspr_b200_unpack(const int8_t *message7, char *hashtab, char *text, size_t text_cap);
+
 /* ---- batched receive chain of one stream (one hydrophone channel) -----------------------
  * The sliding window of lib/sliding_window_stream_to_pdu_impl.cc:98-138 (window k =
  * stream[k*shift*fs, k*shift*fs + fl)) feeding the device `batch_windows` windows per

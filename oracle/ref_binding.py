@@ -93,6 +93,10 @@ def lib():
         L.ref_sw_free.argtypes = [C.c_void_p]
         L.ref_sw_work.restype = C.c_int
         L.ref_sw_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_unpk.restype = C.c_int
+        L.ref_unpk.argtypes = [C.c_void_p] * 4
+        L.ref_nhash.restype = C.c_uint
+        L.ref_nhash.argtypes = [C.c_void_p, C.c_size_t, C.c_uint]
         assert L.ref_candidate_size() == 48
         _lib = L
     return _lib
@@ -246,3 +250,22 @@ def pr3():
     out = np.zeros(162, np.uint8)
     lib().ref_pr3(_p(out))
     return out
+
+
+class RefUnpacker:
+    """uwspr.WSPR_unpacker's unpk_ (lib/helpers.cc:494-590) with its 32768-entry callsign hash table"""
+
+    def __init__(self):
+        self.hashtab = np.zeros(32768 * 13, np.uint8)
+
+    def unpack(self, message7):
+        m = np.ascontiguousarray(message7, dtype=np.uint8)
+        clp = np.zeros(64, np.uint8)
+        cs = np.zeros(32, np.uint8)
+        noprint = lib().ref_unpk(_p(m), _p(self.hashtab), _p(clp), _p(cs))
+        return noprint, bytes(clp).split(b"\0")[0].decode("latin1")
+
+
+def nhash(key, initval=146):
+    k = np.frombuffer(key, np.uint8).copy()
+    return int(lib().ref_nhash(_p(k), len(k), initval))

@@ -44,6 +44,7 @@
 #include "FDR_impl.h"
 #include "sync_and_demodulate_impl.h"
 #include "sliding_window_stream_to_pdu_impl.h"
+#include "helpers.h"
 #undef private
 
 using namespace gr::uwspr;
@@ -439,6 +440,22 @@ void ref_pr3(unsigned char *out162)
      * demodulator's view by demodulating nothing: simply copy from the header. */
 #include "pr3.h"
     memcpy(out162, pr3, 162);
+}
+
+/* ---------------- unpacker (lib/helpers.cc:494-590) ---------------- */
+/* hashtab: 32768*13 bytes of caller-owned state; call_loc_pow >= 32 bytes; callsign >= 16 bytes */
+int ref_unpk(const signed char *message7, char *hashtab, char *call_loc_pow, char *callsign)
+{
+    helpers h;
+    char msg[11];
+    memset(msg, 0, sizeof(msg));
+    memcpy(msg, message7, 7);
+    return h.unpk_(msg, hashtab, call_loc_pow, callsign);
+}
+unsigned int ref_nhash(const void *key, size_t length, unsigned int initval)
+{
+    helpers h;
+    return h.nhash(key, length, initval);
 }
 
 /* ---------------- sliding window ---------------- */

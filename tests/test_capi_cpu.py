@@ -93,3 +93,33 @@ def test_shard_ranges():
             sizes = [hi - lo for lo, hi in parts]
             assert max(sizes) - min(sizes) <= 1
     assert stream_span(2, 5, 22500, 45000) == (45000, 4 * 22500 + 45000)
+
+
+def test_unpacker_known_answers(lib):
+    u = ub.WSPR_unpacker()
+    f = lambda h: np.frombuffer(bytes.fromhex(h), np.uint8)  # noqa: E731
+    assert u.unpack(f("d42c73eb3a7780")) == (0, "VE3EMB FN25 30")   # examples/VE3EMB.c2, test_1500_Hz.wav
+    assert u.unpack(f("d42c73eb0d1840")) == (0, "VE3EMB FN42 33")   # examples/150613_1920.wav
+
+
+def test_unpacker_against_reference_all_message_types(lib):
+    """random 50-bit payloads cover type 1, type 2 (prefix/suffix) and type 3 (hashed call) paths, with the
+    callsign hash table evolving identically on both sides (lib/helpers.cc:494-590)"""
+    from oracle import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref not built")
+    mine, ref = ub.WSPR_unpacker(), rb.RefUnpacker()
+    rng = np.random.default_rng(50)
+    kinds = set()
+    for trial in range(20000):
+        m = rng.integers(0, 256, 7).astype(np.uint8)
+        m[6] &= 0xC0
+        if trial % 3 == 0:                     # bias towards valid callsigns / type 1
+            m[:4] = np.frombuffer(bytes.fromhex("d42c73eb"), np.uint8)
+            m[3] = (m[3] & 0xF0) | int(rng.integers(0, 16))
+        a, b = mine.unpack(m), ref.unpack(m)
+        assert a == b, (m.tobytes().hex(), a, b)
+        if b[1]:
+            kinds.add("3" if b[1].startswith("<") else "2" if "/" in b[1] else "1")
+    assert kinds == {"1", "2", "3"}
+    assert np.array_equal(mine.hashtab, ref.hashtab)
