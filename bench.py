@@ -74,10 +74,11 @@ def gen_windows_torch(nwin, seed, device, maxdrift=3.0, batch=500):
         sigma = np.sqrt((375.0 / 2500.0) / 10 ** (snr / 10.0) / 2.0)
         noise = torch.randn((nb, FL, 2), generator=gen, device=device, dtype=torch.float32)
         x = torch.view_as_complex(noise) * torch.from_numpy(sigma.astype(np.float32)).to(device)[:, None]
-        for i in range(nb):
-            s0 = int(start[i])
-            n = min(FL - s0, 162 * 256)
-            x[i, s0:s0 + n] += sig[i, :n]
+        # add frame i at sample start[i] (one vectorised scatter-add for the batch)
+        pos = torch.from_numpy(start).to(device)[:, None] + k[None, :]
+        ok = pos < FL
+        flat = (torch.arange(nb, device=device)[:, None] * FL + pos)[ok]
+        torch.view_as_real(x).view(-1, 2).index_add_(0, flat, torch.view_as_real(sig)[ok])
         out[b0:b0 + nb] = x
         truth += [dict(msg=m, f0=a, drift=d, start=int(s), snr=q) for m, a, d, s, q in zip(msgs, f0, drift, start, snr)]
     return out, truth
