@@ -351,7 +351,7 @@ def run_ours(args):
     fine_ms = float(st[2])
     alg_flops = nwin * FLOP_SPEC + ncand * FLOP_COARSE + evals * FLOP_POINT
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         cpu = cpu_reference_run(xs_host, min(nwin, max(cores, 24 * cores)), cores)
     line = dict(

@@ -26,6 +26,21 @@ void check(uwspr_b200_ctx *ctx, int st)
 
 }  // namespace
 
+std::string format_message_log(int framecount, const uwspr_b200_candidate_t &c, const int8_t blob[7])
+{
+    char buf[512];
+    int n = snprintf(buf, sizeof(buf), "Frame: %d\nBaseband freq is %2.2f Hz\n(6 Hz) SNR is %2.2f dB\n", framecount, c.freq, c.snr);
+    if (c.m_type == 0)
+        n += snprintf(buf + n, sizeof(buf) - n, "Linear drift is %2.2f Hz\n", c.m_linear.drift);
+    else  // the reference does not end this line
+        n += snprintf(buf + n, sizeof(buf) - n, "Nonlinear drift  V=:(%2.2f,%2.2f) p=(%d,%d)", c.m_nonlinear.V1,
+                      c.m_nonlinear.V2, c.m_nonlinear.p1, c.m_nonlinear.p2);
+    n += snprintf(buf + n, sizeof(buf) - n, "Data: ");
+    for (int i = 0; i < 7; i++) n += snprintf(buf + n, sizeof(buf) - n, "%02x", (unsigned)(unsigned char)blob[i]);
+    snprintf(buf + n, sizeof(buf) - n, "\n\n");
+    return std::string(buf);
+}
+
 // ------------------------------------------------------------------------------ FDR
 FDR::sptr FDR::make(int fs, int fl, int spb, int maxdrift, int maxfreqs, int halfbandwidth, int cf, int threshold)
 {
@@ -63,7 +78,21 @@ sync_and_demodulate::sptr sync_and_demodulate::make(int fs, int fl, int spb, int
     return b;
 }
 
-sync_and_demodulate::~sync_and_demodulate() { uwspr_b200_destroy(d_ctx); }
+sync_and_demodulate::~sync_and_demodulate()
+{
+    if (d_log) fclose(d_log);
+    uwspr_b200_destroy(d_ctx);
+}
+
+void sync_and_demodulate::set_message_log(const std::string &path)
+{
+    if (d_log) fclose(d_log);
+    d_log = fopen(path.c_str(), "a");  // :98
+    if (!d_log) throw std::runtime_error("cannot open message log " + path);  // the reference dereferences NULL here
+    time(&d_start);
+    fprintf(d_log, "Start time: %s\n", asctime(localtime(&d_start)));  // :105-107
+    fflush(d_log);
+}
 
 void sync_and_demodulate::demodulate(const candidates_pdu &pdu)
 {
@@ -84,6 +113,15 @@ void sync_and_demodulate::demodulate(const candidates_pdu &pdu)
                                         &soft[(size_t)j * UWSPR_B200_NJIG * UWSPR_B200_NSYM], UWSPR_B200_NJIG, m.blob, &idt,
                                         &cycles)) {
             d_framecount++;  // :492
+            if (d_log) {     // :507-526
+                time_t now;
+                time(&now);
+                const long dt = (long)difftime(now, d_start);
+                fprintf(d_log, "Handoff time : %sElapsed time: %02d:%02d:%02d\n", asctime(localtime(&now)),
+                        (int)((dt / 3600) % 24), (int)((dt / 60) % 60), (int)(dt % 60));
+                fputs(format_message_log(d_framecount, pdu.candidates[j], m.blob).c_str(), d_log);
+                fflush(d_log);
+            }
             m.candidate = pdu.candidates[j];
             m.window = -1;
             if (d_out) d_out(m);  // :528-530
@@ -248,6 +286,16 @@ int uwspr_b200_receiver_pop(uwspr_b200_receiver *rx, int8_t *message7, int64_t *
     if (window) *window = m.window;
     if (cand) *cand = m.candidate;
     return 1;
+}
+
+int uwspr_b200_format_message_log(int framecount, const uwspr_b200_candidate_t *cand, const int8_t *message7, char *text,
+                                  size_t text_cap)
+{
+    if (!cand || !message7 || !text) return UWSPR_B200_E_PARAM;
+    const std::string s = gr::uwspr::format_message_log(framecount, *cand, message7);
+    if (s.size() + 1 > text_cap) return UWSPR_B200_E_CAPACITY;
+    memcpy(text, s.c_str(), s.size() + 1);
+    return UWSPR_B200_OK;
 }
 
 int64_t uwspr_b200_receiver_windows(const uwspr_b200_receiver *rx)

@@ -20,6 +20,8 @@
 
 #include <complex>
 #include <cstdint>
+#include <cstdio>
+#include <ctime>
 #include <deque>
 #include <functional>
 #include <memory>
@@ -47,6 +49,10 @@ struct message_pdu {
     uwspr_b200_candidate_t candidate;  // not in the reference's PDU; kept for logging
     int64_t window;                    // index of the window it came from (receiver only)
 };
+
+// text the reference appends to messagelog.txt for one decoded frame, without the two
+// wall-clock lines ("Handoff time", "Elapsed time") that precede it (sync_and_demodulate_impl.cc:508-525)
+std::string format_message_log(int framecount, const uwspr_b200_candidate_t &cand, const int8_t blob[7]);
 
 class context_error : public std::runtime_error
 {
@@ -82,11 +88,16 @@ public:
     // message handler of port "in": one message_pdu per decoded candidate, in candidate order
     void demodulate(const candidates_pdu &pdu);
     int framecount() const { return d_framecount; }
+    // the reference appends every decode to ./messagelog.txt (sync_and_demodulate_impl.cc:98-108,
+    // :507-526); off by default here, same text when enabled
+    void set_message_log(const std::string &path);
 
 private:
     sync_and_demodulate() {}
     uwspr_b200_ctx *d_ctx = nullptr;
     int d_fl = 0, d_framecount = 0;
+    FILE *d_log = nullptr;
+    time_t d_start = 0;
     std::function<void(const message_pdu &)> d_out;
 };
 

@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_host_free", "uwspr_b200_set_stream", "uwspr_b200_set_debug", "uwspr_b200_debug_spectrogram",
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
-    "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack",
+    "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack", "uwspr_b200_format_message_log",
 ]
 
 CAND_DTYPE = np.dtype(
@@ -54,7 +54,8 @@ class UwsprError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(_HERE), "libuwspr_b200.so")
+    # UWSPR_B200_LIB selects another build of the same library (kernel tuning experiments)
+    return os.environ.get("UWSPR_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libuwspr_b200.so")
 
 
 _lib = None
@@ -382,6 +383,21 @@ class Receiver:
             self.close()
         except Exception:
             pass
+
+
+def format_message_log(framecount, cand, message7):
+    """the text the reference appends to messagelog.txt for a decoded frame (without its two clock lines)"""
+    L = load_library()
+    L.uwspr_b200_format_message_log.restype = C.c_int
+    L.uwspr_b200_format_message_log.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    c = np.zeros(1, CAND_DTYPE)
+    c[0] = cand
+    m = np.ascontiguousarray(message7, dtype=np.uint8)
+    text = np.zeros(512, np.uint8)
+    st = L.uwspr_b200_format_message_log(framecount, _p(c), _p(m), _p(text), text.size)
+    if st != 0:
+        raise UwsprError(st, L.uwspr_b200_status_string(st).decode())
+    return bytes(text).split(b"\0")[0].decode("latin1")
 
 
 class WSPR_unpacker:

@@ -187,6 +187,11 @@ UWSPR_B200_API int uwspr_b200_decode_candidate(const uwspr_b200_refined_t *refin
 UWSPR_B200_API size_t uwspr_b200_hashtab_bytes(void);
 UWSPR_B200_API int uwspr_b200_unpack(const int8_t *message7, char *hashtab, char *text, size_t text_cap);
 
+/* The text the reference appends to messagelog.txt for one decoded frame
+ * (lib/sync_and_demodulate_impl.cc:508-525), without the two wall-clock lines before it. */
+UWSPR_B200_API int uwspr_b200_format_message_log(int framecount, const uwspr_b200_candidate_t *cand,
+                                                 const int8_t *message7, char *text, size_t text_cap);
+
 /* ---- batched receive chain of one stream (one hydrophone channel) -----------------------
  * The sliding window of lib/sliding_window_stream_to_pdu_impl.cc:98-138 (window k =
  * stream[k*shift*fs, k*shift*fs + fl)) feeding the device `batch_windows` windows per

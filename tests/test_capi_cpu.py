@@ -95,6 +95,29 @@ def test_shard_ranges():
     assert stream_span(2, 5, 22500, 45000) == (45000, 4 * 22500 + 45000)
 
 
+def test_message_log_text_matches_reference_file(lib, golden, golden_windows, tmp_path):
+    """the reference block appends to ./messagelog.txt on every decode (sync_and_demodulate_impl.cc:507-526);
+    the same candidates and blobs through uwspr_b200_format_message_log give the same lines"""
+    from oracle import ref_binding as rb
+    from uwspr_b200.binding import format_message_log
+    if not rb.available():
+        pytest.skip("oracle/_ref not built")
+    sd = rb.RefSD(logdir=str(tmp_path))
+    want = ""
+    frame = 0
+    for name in ("ve3emb_c2", "mix_whales"):   # a nonlinear and a linear candidate
+        cands = golden[name + "/cands"].view(rb.CAND_DTYPE).reshape(-1)
+        blobs, calls, fanos = sd.demodulate(golden_windows[name], cands)
+        assert len(blobs) == 1
+        frame += 1
+        decoded = cands[0]                     # in both fixtures the first candidate is the one that decodes
+        want += format_message_log(frame, decoded, blobs[0])
+    text = open(tmp_path / "messagelog.txt").read()
+    got = "".join(l + "\n" for l in text.split("\n")[2:] if not l.startswith(("Handoff time", "Elapsed time")))
+    # got now starts after the "Start time" line and its blank line; strip the trailing split artefact
+    assert got.rstrip("\n") + "\n\n" == want
+
+
 def test_unpacker_known_answers(lib):
     u = ub.WSPR_unpacker()
     f = lambda h: np.frombuffer(bytes.fromhex(h), np.uint8)  # noqa: E731
