@@ -60,6 +60,7 @@ struct uwspr_b200_ctx {
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[2] = { nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int last_cw = 0;
+    int dev_chunks = 1;
     bool last_host = false;
     std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -255,7 +256,13 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     // compute streams, so the H2D copy of chunk c+1 and the tail of chunk c-1's kernels overlap
     // the kernels of chunk c.
     const bool host = space == UWSPR_B200_HOST;
-    const int cw = host ? std::max(1, std::min(1024, ctx->chunk_windows / 2)) : ctx->chunk_windows;
+    // dev_chunks > 1 (tuning knob, UWSPR_B200_DEV_CHUNKS): device input is also split over the two
+    // sets/streams so that one chunk's spectrogram/coarse kernels fill idle issue slots of the
+    // previous chunk's fine kernel
+    const bool two = host || ctx->dev_chunks > 1;
+    const int cw = host ? std::max(1, std::min(1024, ctx->chunk_windows / 2))
+                        : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + ctx->dev_chunks - 1) / ctx->dev_chunks))
+                               : ctx->chunk_windows);
     const int nchunks = (nwin + cw - 1) / cw;
     if (nchunks > kMaxChunks) return fail(ctx, UWSPR_B200_E_PARAM, "too many chunks: raise max_windows");
     while ((int)ctx->ev.size() < 4 * nchunks) {
@@ -263,7 +270,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         CU(cudaEventCreate(&e));
         ctx->ev.push_back(e);
     }
-    cudaStream_t streams[2] = { cs, host && nchunks > 1 ? ctx->compute2 : cs };
+    cudaStream_t streams[2] = { cs, two && nchunks > 1 ? ctx->compute2 : cs };
     CU(cudaEventRecord(ctx->ev_begin, cs));
     CU(cudaMemsetAsync(b.counters, 0, 16 * sizeof(int), cs));
     if (!do_coarse) {
@@ -289,7 +296,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     }
     for (int c = 0; c < nchunks; c++) {
         const int w0 = c * cw, nw = std::min(cw, nwin - w0);
-        const int s = host ? (c & 1) : 0;
+        const int s = two ? (c & 1) : 0;
         cudaStream_t st = streams[s];
         const float2 *xdev;
         if (host) {
@@ -343,7 +350,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         CU(cudaStreamWaitEvent(cs, ctx->ev_join, 0));
     }
     ctx->last_cw = cw;
-    ctx->last_host = host;
+    ctx->last_host = two;
     int h_counters[4];
     CU(cudaMemcpyAsync(h_counters, b.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, cs));
     CU(cudaStreamSynchronize(cs));
@@ -456,6 +463,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     UwDims &d = ctx->d;
     ctx->max_windows = p.max_windows > 0 ? p.max_windows : 1;
     ctx->chunk_windows = std::min(ctx->max_windows, 16384);
+    if (const char *e = getenv("UWSPR_B200_DEV_CHUNKS")) ctx->dev_chunks = std::max(1, atoi(e));
     const long long def_cap = (long long)ctx->max_windows * d.maxcand;
     ctx->max_candidates = p.max_candidates > 0 ? p.max_candidates : (int)std::min<long long>(def_cap, 1 << 22);
     Buffers &b = ctx->b;
