@@ -37,6 +37,10 @@ for p in (ROOT, os.path.join(ROOT, "gr-uwspr_b200")):
 import numpy as np  # noqa: E402
 
 FL = 45000
+try:
+    _ALL_CPUS = set(os.sched_getaffinity(0))
+except Exception:
+    _ALL_CPUS = set(range(os.cpu_count() or 1))
 PARAMS = dict(fs=375, fl=FL, spb=256, maxdrift=4, maxfreqs=200, halfbandwidth=10, cf=1500, threshold=10)
 METRIC = "WSPR windows/sec (coarse+fine sync+demod)"
 FLOP_SPEC, FLOP_COARSE, FLOP_POINT = 9.09e6, 5 * 26 * (2 * PARAMS["maxdrift"] + 126) * 162 * 9.0, 1.327e6
@@ -198,6 +202,29 @@ def recorded_traffic(nwin):
     return None
 
 
+def bind_to_gpu_numa_node(local):
+    """pins this rank to the CPUs of the NUMA node its GPU hangs off, so that the pinned host
+    buffers it allocates next are local to the GPU's PCIe root (first touch).  Best effort."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -211,7 +238,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import testdata as td
-    cores = os.cpu_count() or 1
+    cores = len(_ALL_CPUS) or os.cpu_count() or 1
     n = min(args.windows, max(cores, args.ref_windows_per_core * cores))
     xs = np.stack([td.synth_window(1000, w, maxdrift=3.0)[0] for w in range(min(n, 4 * cores))])
     # the sample is tiled from a few hundred distinct windows: CPU time per window is data independent
@@ -245,8 +272,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     dev = torch.device("cuda", local)
     nwin = args.windows
     ctx = ub.Context(device=local, max_windows=nwin, max_candidates=max(4 * nwin, 1024), **PARAMS)
@@ -352,14 +382,18 @@ def run_ours(args):
     alg_flops = nwin * FLOP_SPEC + ncand * FLOP_COARSE + evals * FLOP_POINT
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
-        cores = os.cpu_count() or 1
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)  # undo the NUMA pinning: the baseline uses every core
+        except Exception:
+            pass
+        cores = len(_ALL_CPUS) or os.cpu_count() or 1
         cpu = cpu_reference_run(xs_host, min(nwin, max(cores, 24 * cores)), cores)
     line = dict(
         metric=METRIC, value=value, unit="windows/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload="10k synthetic WSPR windows swept over SNR -30..0 dB with random drift, 1 B200 (BASELINE.json configs[2]); per GPU",
                     windows_per_gpu=nwin, input_bytes_per_gpu=h2d, l2="inputs larger than L2 (3.6 GB vs 126 MB)",
-                    jiggles="all 17 per gated candidate", candidates=ncand, gated=gated, sync_evaluations=evals,
+                    jiggles="all 17 per gated candidate", host_numa_node=numa, candidates=ncand, gated=gated, sync_evaluations=evals,
                     **{k: PARAMS[k] for k in ("maxdrift", "halfbandwidth", "threshold", "maxfreqs")}),
         e2e=dict(value=e2e_value, unit="windows/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(d2h), ms_per_step=ms_e2e / args.steps,
                  pcie_h2d_gbs=pcie_gbs, pcie_bound_windows_per_s=world * pcie_gbs * 1e9 / (FL * 8)),
