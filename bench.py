@@ -415,6 +415,12 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly one JSON line.  Libraries (NCCL prints its version with printf) write to
+    # file descriptor 1, so fd 1 is pointed at stderr and Python's sys.stdout keeps the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

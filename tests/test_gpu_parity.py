@@ -336,3 +336,24 @@ def test_parity_at_scale_256_windows():
         recovered += any(bytes(m) == bytes(metas[w]["msg"]) for _, m, _ in msgs)
     assert recovered >= 0.9 * nwin
     ctx.close()
+
+
+@pytest.mark.parametrize("maxfreqs,threshold,maxdrift", [(3, 10, 0), (200, 1, 2), (200, 1000000, 1), (2, 3, 4)])
+def test_candidate_cap_and_threshold_variants(maxfreqs, threshold, maxdrift):
+    """maxfreqs caps the peak list in bin order before the snr sort (FDR_impl.cc:296-305); the
+    nonlinear/linear threshold changes which hypothesis the ordered update rule keeps (:360,:392)"""
+    x = sum(td.synth_window(13, w, snr_db=-9.0 - 2 * w, f0=f0)[0] for w, f0 in enumerate([-31.0, -12.0, 6.5, 29.0]))
+    kw = dict(halfbandwidth=40, maxfreqs=maxfreqs, threshold=threshold, maxdrift=maxdrift)
+    ctx = ub.Context(max_windows=1, **kw)
+    ctx.set_debug(True)
+    npk, cands = ctx.coarse(x.reshape(1, -1))
+    of = ob.OracleFDR(**kw)
+    want, *_ = oracle_on_gpu_ps(of, ctx, x, 0)
+    assert npk[0] == len(want) == min(maxfreqs, len(want))
+    assert cands_equal_exact(cands, want)
+    if threshold == 1:
+        assert (cands["m_type"] == 1).any()      # a ratio of 1 lets trajectories displace the linear hits
+    if threshold == 1000000:
+        assert (cands["m_type"] == 0).all()
+    check_fine_against_oracle(ctx, x, want[:3])
+    ctx.close()
