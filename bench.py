@@ -404,7 +404,7 @@ def run_ours(args):
                     jiggles="all 17 per gated candidate", host_numa_node=numa, candidates=ncand, gated=gated, sync_evaluations=evals,
                     **{k: PARAMS[k] for k in ("maxdrift", "halfbandwidth", "threshold", "maxfreqs")}),
         e2e=dict(value=e2e_value, unit="windows/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(d2h), ms_per_step=ms_e2e / args.steps,
-                 pcie_h2d_gbs=pcie_gbs, pcie_bound_windows_per_s=world * pcie_gbs * 1e9 / (FL * 8)),
+                 pcie_h2d_gbs=pcie_gbs, pcie_bound_windows_per_s=world * pcie_gbs * 1e9 / (h2d / nwin)),
         gpu_launches=int(launches),
         stage_ms=dict(spectrogram_normalizer=float(st[0]), coarse_search=float(st[1]), fine_sync_demod=fine_ms, call=float(st[3])),
         roofline=dict(bound="hbm", kernel="k_fine (fine sync + soft symbols)", achieved=alg_bytes / (fine_ms * 1e-3) / 1e9, peak=hbm_peak,
