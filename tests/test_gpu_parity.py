@@ -357,3 +357,26 @@ def test_candidate_cap_and_threshold_variants(maxfreqs, threshold, maxdrift):
         assert (cands["m_type"] == 0).all()
     check_fine_against_oracle(ctx, x, want[:3])
     ctx.close()
+
+
+def test_staged_jiggles_equal_the_full_set(golden_windows):
+    """fine(jig 0..0) followed by fine(jig 1..16) for the candidates that did not decode
+    returns exactly the soft symbols of the eager 17-jiggle call; odd ranges exercise the generic lag loop"""
+    ctx = ctx_for(maxdrift=4)
+    xs = np.stack([golden_windows["mix_whales"], td.synth_window(0, 4, snr_db=-29.0)[0], td.synth_window(0, 7, snr_db=-23.0)[0]])
+    npk, cands = ctx.coarse(xs)
+    full = ctx.fine(xs, npk, cands)
+    first = ctx.fine(xs, npk, cands, jig_first=0, jig_count=1)
+    rest = ctx.fine(xs, npk, cands, jig_first=1, jig_count=16)
+    mid = ctx.fine(xs, npk, cands, jig_first=5, jig_count=7)
+    for k in range(3):  # refined, jig, soft
+        if k == 0:
+            assert full[0].tobytes() == first[0].tobytes() == rest[0].tobytes() == mid[0].tobytes()
+            continue
+        assert np.array_equal(full[k][:, 0:1], first[k])
+        assert np.array_equal(full[k][:, 1:17], rest[k])
+        assert np.array_equal(full[k][:, 5:12], mid[k])
+    # and the candidate list left on the device by coarse() is the one fine(cands=None) uses
+    again = ctx.fine(xs, jig_first=0, jig_count=17)
+    t = len(cands)
+    assert again[2][:t].tobytes() == full[2].tobytes()
