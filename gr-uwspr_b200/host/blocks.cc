@@ -192,19 +192,24 @@ void receiver::run_batch(int nwin)
     check(d_ctx, uwspr_b200_coarse_fine(d_ctx, reinterpret_cast<const float *>(d_stream.data()), UWSPR_B200_HOST, d_stride,
                                         nwin, 0, UWSPR_B200_NJIG, d_npk.data(), d_cands.data(), d_cap, &total,
                                         d_refined.data(), d_jig.data(), d_soft.data()));
+    int ncand = 0;
+    for (int w = 0; w < nwin; w++) ncand += d_npk[w];
+    // the decoder of every candidate of the batch, spread over the host cores; messages are
+    // still published in (window, candidate) order
+    std::vector<uint8_t> decoded((size_t)ncand);
+    std::vector<int8_t> blobs((size_t)ncand * 7);
+    if (uwspr_b200_decode_batch(d_refined.data(), d_jig.data(), d_soft.data(), ncand, UWSPR_B200_NJIG, 0,
+                                decoded.data(), blobs.data(), nullptr, nullptr) < 0)
+        throw context_error(UWSPR_B200_E_PARAM, "uwspr_b200_decode_batch failed");
     int g = 0;
     for (int w = 0; w < nwin; w++)
         for (int j = 0; j < d_npk[w]; j++, g++) {
+            if (!decoded[g]) continue;
             message_pdu m;
-            int32_t idt;
-            uint32_t cycles;
-            if (uwspr_b200_decode_candidate(&d_refined[g], &d_jig[(size_t)g * UWSPR_B200_NJIG],
-                                            &d_soft[(size_t)g * UWSPR_B200_NJIG * UWSPR_B200_NSYM], UWSPR_B200_NJIG, m.blob,
-                                            &idt, &cycles)) {
-                m.candidate = d_cands[g];
-                m.window = d_next_window + w;
-                d_msgs.push_back(m);
-            }
+            memcpy(m.blob, &blobs[(size_t)g * 7], 7);
+            m.candidate = d_cands[g];
+            m.window = d_next_window + w;
+            d_msgs.push_back(m);
         }
     // window k = stream[k*shift*fs, k*shift*fs + fl): drop what no later window reads
     d_stream.erase(d_stream.begin(), d_stream.begin() + (size_t)nwin * d_stride);

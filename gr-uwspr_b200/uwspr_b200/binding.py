@@ -12,7 +12,8 @@ HOST, DEVICE = 0, 1
 EXPORTED_SYMBOLS = [
     "uwspr_b200_create", "uwspr_b200_destroy", "uwspr_b200_last_error", "uwspr_b200_status_string",
     "uwspr_b200_create_error", "uwspr_b200_info", "uwspr_b200_coarse", "uwspr_b200_fine", "uwspr_b200_coarse_fine",
-    "uwspr_b200_deinterleave", "uwspr_b200_fano", "uwspr_b200_decode_candidate", "uwspr_b200_host_alloc",
+    "uwspr_b200_deinterleave", "uwspr_b200_fano", "uwspr_b200_decode_candidate", "uwspr_b200_decode_batch",
+    "uwspr_b200_host_alloc",
     "uwspr_b200_host_free", "uwspr_b200_set_stream", "uwspr_b200_set_debug", "uwspr_b200_debug_spectrogram",
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
@@ -93,6 +94,8 @@ def load_library():
     L.uwspr_b200_fano.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_uint32]
     L.uwspr_b200_decode_candidate.restype = C.c_int
     L.uwspr_b200_decode_candidate.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
+    L.uwspr_b200_decode_batch.restype = C.c_int
+    L.uwspr_b200_decode_batch.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
     L.uwspr_b200_host_alloc.restype = C.c_int
     L.uwspr_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.uwspr_b200_host_free.argtypes = [vp]
@@ -295,22 +298,25 @@ def fano(symbols, delta=60, maxcycles=10000, nbits=81):
     return r, data, metric.value, cycles.value, maxnp.value
 
 
-def decode_candidates(refined, jig, soft):
-    """the peak-up/decode loop (sync_and_demodulate_impl.cc:457-490) over fetched results;
-    returns a list of (candidate index, 7-byte message, idt used)"""
+def decode_candidates(refined, jig, soft, nthreads=0):
+    """the peak-up/decode loop (sync_and_demodulate_impl.cc:457-490) over fetched results, spread over
+    `nthreads` host threads (0: all cores); returns a list of (candidate index, 7-byte message, idt used)
+    in candidate order"""
     L = load_library()
-    out = []
     jig = np.ascontiguousarray(jig)
     soft = np.ascontiguousarray(soft)
     refined = np.ascontiguousarray(refined)
-    for g in range(len(refined)):
-        msg = np.zeros(7, np.int8)
-        idt, cyc = C.c_int32(), C.c_uint32()
-        ok = L.uwspr_b200_decode_candidate(_p(refined[g:g + 1]), _p(jig[g]), _p(soft[g]), jig.shape[1], _p(msg),
-                                           C.byref(idt), C.byref(cyc))
-        if ok:
-            out.append((g, msg.view(np.uint8).copy(), idt.value))
-    return out
+    n = len(refined)
+    if n == 0:
+        return []
+    decoded = np.zeros(n, np.uint8)
+    msgs = np.zeros((n, 7), np.int8)
+    idt = np.zeros(n, np.int32)
+    got = L.uwspr_b200_decode_batch(_p(refined), _p(jig), _p(soft), n, jig.shape[1], int(nthreads), _p(decoded),
+                                    _p(msgs), _p(idt), None)
+    if got < 0:
+        raise UwsprError(-got, L.uwspr_b200_status_string(-got).decode())
+    return [(int(g), msgs[g].view(np.uint8).copy(), int(idt[g])) for g in np.flatnonzero(decoded)]
 
 
 class FDR:

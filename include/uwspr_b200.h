@@ -178,6 +178,17 @@ UWSPR_B200_API int uwspr_b200_decode_candidate(const uwspr_b200_refined_t *refin
                                                const uwspr_b200_jiggle_t *jig, const uint8_t *soft,
                                                int jig_count, int8_t *message7, int32_t *idt_used,
                                                uint32_t *fano_cycles);
+/* The same loop over `ncand` candidates as uwspr_b200_fine() returns them (refined[ncand],
+ * jig[ncand][jig_count], soft[ncand][jig_count][162]), spread over `nthreads` host threads
+ * (<= 0: one per online core).  Candidates are independent in the reference too (one
+ * demodulate() loop iteration each, :405), so the outputs do not depend on the thread count:
+ * decoded[g] = 0/1, messages[g*7..], idt_used[g], fano_cycles[g] (the last two may be NULL).
+ * Returns the number of decoded candidates, or a negative status. */
+UWSPR_B200_API int uwspr_b200_decode_batch(const uwspr_b200_refined_t *refined,
+                                           const uwspr_b200_jiggle_t *jig, const uint8_t *soft,
+                                           int64_t ncand, int jig_count, int nthreads,
+                                           uint8_t *decoded, int8_t *messages7, int32_t *idt_used,
+                                           uint32_t *fano_cycles);
 
 /* ---- WSPR_unpacker's text: lib/helpers.cc:494-590 (unpk_) -------------------------------
  * message7 -> "CALL GRID dBm" (type 1), "PFX/CALL dBm" (type 2) or "<CALL> GRID6 dBm" (type 3).

@@ -146,3 +146,54 @@ def test_unpacker_against_reference_all_message_types(lib):
             kinds.add("3" if b[1].startswith("<") else "2" if "/" in b[1] else "1")
     assert kinds == {"1", "2", "3"}
     assert np.array_equal(mine.hashtab, ref.hashtab)
+
+
+def test_decode_batch_equals_candidate_loop_for_any_thread_count(lib):
+    """uwspr_b200_decode_batch == one uwspr_b200_decode_candidate per candidate == the oracle's decoder
+    driven by the reference's gate (sync_and_demodulate_impl.cc:457-490), for 1, 3 and all host threads"""
+    rng = np.random.default_rng(5)
+    n, nj = 150, 17
+    refined = np.zeros(n, ub.REFINED_DTYPE)
+    jig = np.zeros((n, nj), ub.JIG_DTYPE)
+    soft = rng.integers(0, 256, (n, nj, 162)).astype(np.uint8)
+    sent = np.zeros((n, 7), np.uint8)
+    refined["worth_a_try"] = rng.random(n) < 0.9
+    jig["gate"] = rng.random((n, nj)) < 0.7
+    for g in range(n):
+        data = np.zeros(11, np.uint8)
+        data[:7] = sent[g] = td.message_bytes(rng)
+        clean = np.where(ob.encode(data)[:162] == 1, 200, 56).astype(np.uint8)
+        # interleave: the decoder de-interleaves what it is handed
+        tx = np.zeros(162, np.uint8)
+        tx[ub.deinterleave(np.arange(162, dtype=np.uint8))] = clean
+        first_good = rng.integers(0, nj + 6)          # >= nj: never decodable
+        for t in range(first_good, nj):
+            s = tx.copy()
+            hit = rng.integers(0, 162, rng.integers(0, 12))
+            s[hit] = rng.integers(0, 256, len(hit))
+            soft[g, t] = s
+    want = {}
+    for g in range(n):
+        if not refined["worth_a_try"][g]:
+            continue
+        for t in range(nj):
+            if not jig["gate"][g, t]:
+                continue
+            r, data, *_ = ob.fano(ub.deinterleave(soft[g, t]))
+            if r == 0:
+                want[g] = (bytes(data[:7]), t)
+                break
+    assert 30 < len(want) < n
+    L = lib
+    single = {}
+    for g in range(n):
+        msg = np.zeros(7, np.int8)
+        idt = C.c_int32()
+        if L.uwspr_b200_decode_candidate(ub.binding._p(refined[g:g + 1]), ub.binding._p(jig[g]), ub.binding._p(soft[g]),
+                                         nj, ub.binding._p(msg), C.byref(idt), None):
+            single[g] = (msg.tobytes(), idt.value)
+    assert single == want
+    for nthreads in (1, 3, 0):
+        got = {g: (m.tobytes(), t) for g, m, t in ub.decode_candidates(refined, jig, soft, nthreads=nthreads)}
+        assert got == want
+    assert ub.decode_candidates(refined[:0], jig[:0], soft[:0]) == []
