@@ -94,6 +94,30 @@ def synth_batch(nwin, stream=0, first=0, **kw):
     return xs, metas
 
 
+def synth_array(nchan, window, whales, stream=5, snr_db=-18.0, whale_gain=1.0, fl=FL, seed=SEED_BASE):
+    """BASELINE.json configs[4]: one transmitted frame seen by `nchan` hydrophones --
+    per-channel delay U{0..64} samples and gain U(0.05, 0.2), independent AWGN at `snr_db` relative to a
+    unit-amplitude frame (2500 Hz convention) scaled with the mean gain, plus `whales` (375-sps complex,
+    looped, per-channel circular offset) at `whale_gain` (the x1 / x0.1 ratio of
+    examples/WaveFilePlusNoiseDecode.grc:586,637).  Returns (x [nchan, fl] complex64, meta)."""
+    rng = np.random.default_rng([seed, stream, window, 64])
+    msg = message_bytes(rng)
+    syms = ob.channel_symbols(msg)
+    f0 = float(rng.uniform(-6, 6))
+    start = int(375 + rng.integers(0, 2400))
+    delays = rng.integers(0, 65, nchan)
+    gains = rng.uniform(0.05, 0.2, nchan)
+    offs = rng.integers(0, len(whales), nchan)
+    sigma2 = (375.0 / 2500.0) / 10 ** (snr_db / 10.0) * 0.125 ** 2
+    x = np.empty((nchan, fl), np.complex64)
+    for c in range(nchan):
+        sig = modulate(syms, f0, 0.0, start + int(delays[c]), amp=float(gains[c]), fl=fl)
+        noise = (rng.standard_normal(fl) + 1j * rng.standard_normal(fl)) * np.sqrt(sigma2 / 2.0)
+        wh = np.take(whales, (offs[c] + np.arange(fl)) % len(whales))
+        x[c] = (sig + noise + whale_gain * wh).astype(np.complex64)
+    return x, dict(msg=msg, f0=f0, start=start, delays=delays, gains=gains)
+
+
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 

@@ -9,6 +9,7 @@ Outputs (committed; the GPU box has no /root/reference):
   win_<name>.npy   four 375-sps complex64 windows derived from the reference fixtures
                    (examples/VE3EMB.c2 conjugated as lib/c2file_source_impl.cc:91 does;
                    the wavs through oracle.testdata.frontend)
+  whales_375sps.npy  channel 0 of examples/whales_12000sps.wav through the same front-end
   golden.npz       per case: reference candidates, the per-call refinement trace, the
                    decoder records, the published 7-byte blobs, spectrogram probes;
                    plus known-answer vectors for the SLM model, the encoder, the
@@ -49,7 +50,19 @@ def fanos_array(fanos):
     return a
 
 
+def write_whales():
+    """channel 0 of examples/whales_12000sps.wav at 375 sps (the interference of BASELINE.json configs[4];
+    oracle.testdata.synth_array loops it)"""
+    w, _ = td.read_wav(EX + "whales_12000sps.wav")
+    y = td.frontend(w[:, 0]).astype(np.complex64)
+    np.save(os.path.join(OUT, "whales_375sps.npy"), y)
+    print("whales_375sps", y.shape, float(np.sqrt((np.abs(y) ** 2).mean())))
+
+
 def main():
+    write_whales()
+    if "--whales-only" in sys.argv:
+        return
     wins = {}
     wins["ve3emb_c2"] = td.load_c2(EX + "VE3EMB.c2")
     a, _ = td.read_wav(EX + "test_1500_Hz.wav")

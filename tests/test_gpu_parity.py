@@ -380,3 +380,45 @@ def test_staged_jiggles_equal_the_full_set(golden_windows):
     again = ctx.fine(xs, jig_first=0, jig_count=17)
     t = len(cands)
     assert again[2][:t].tobytes() == full[2].tobytes()
+
+
+def test_hydrophone_array_with_whale_noise():
+    """BASELINE.json configs[4] at test size: 16 channels x 2 windows of a synthetic hydrophone array (one frame
+    per window, per-channel delay and gain, independent noise, looped whale recording as interference), flattened
+    (channel, window) -> one submission; every channel bit-exact against the oracle chain"""
+    whales = np.load(td.golden_path("whales_375sps.npy"))
+    nchan, nwin = 16, 2
+    xs, metas = [], []
+    for w in range(nwin):
+        x, meta = td.synth_array(nchan, w, whales, snr_db=-21.0)
+        xs.append(x)
+        metas.append(meta)
+    flat = np.stack(xs, axis=1).reshape(nchan * nwin, -1)   # index = channel * nwin + window
+    ctx = ctx_for(maxdrift=0, max_windows=nchan * nwin)
+    ctx.set_debug(True)
+    npk, cands, refined, jig, soft = ctx.coarse_fine(flat)
+    base = np.concatenate([[0], np.cumsum(npk)])
+    of = ob.OracleFDR(maxdrift=0)
+    heard = np.zeros((nchan, nwin), bool)
+    for i in range(nchan * nwin):
+        c, w = divmod(i, nwin)
+        want, *_ = oracle_on_gpu_ps(of, ctx, flat[i], i)
+        got = cands[base[i]:base[i + 1]]
+        assert cands_equal_exact(got, want)
+        o_ref, o_jigs = ob.demodulate_full(flat[i], want)
+        for j in range(len(want)):
+            g = base[i] + j
+            assert refined["f1"][g].tobytes() == o_ref[j, 0].tobytes() and refined["shift1"][g] == int(o_ref[j, 1])
+            for t, call in enumerate(o_jigs[j]):
+                assert np.array_equal(soft[g, t], np.frombuffer(bytes(call.symbols), np.uint8))
+        sl = slice(base[i], base[i + 1])
+        msgs = ub.decode_candidates(refined[sl], jig[sl], soft[sl])
+        oblobs, _, _ = ob.demodulate(flat[i], want)
+        assert np.array([m for _, m, _ in msgs], np.uint8).reshape(-1, 7).tobytes() == oblobs.tobytes()
+        heard[c, w] = any(np.array_equal(m, metas[w]["msg"]) for _, m, _ in msgs)
+        # the refined shift follows the channel's delay to within a few of the 16-sample lag steps searched
+        if heard[c, w]:
+            j = [k for k, (_, m, _) in enumerate(msgs) if np.array_equal(m, metas[w]["msg"])][0]
+            g = base[i] + msgs[j][0]
+            assert abs(int(refined["shift1"][g]) - (metas[w]["start"] + int(metas[w]["delays"][c]))) <= 48
+    assert heard.mean() > 0.7

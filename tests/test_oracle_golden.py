@@ -109,3 +109,15 @@ def test_sliding_window_count():
     assert ob.sliding_window_count(45000, 45000) == 1
     assert ob.sliding_window_count(45000 + 3375, 1125) == 2
     assert ob.sliding_window_count(44999, 4096) == 0
+
+
+def test_array_fixture_decodes_on_the_oracle():
+    """the hydrophone-array generator (BASELINE.json configs[4]) and its whale fixture: every channel
+    of a small array carries the same decodable frame"""
+    whales = np.load(td.golden_path("whales_375sps.npy"))
+    assert whales.dtype == np.complex64 and whales.shape == (24241,)
+    x, meta = td.synth_array(3, 0, whales, snr_db=-15.0)
+    of = ob.OracleFDR(maxdrift=0)
+    for c in range(3):
+        blobs, _, _ = ob.demodulate(x[c], of.transform(x[c]))
+        assert any(bytes(b) == bytes(meta["msg"]) for b in blobs)
