@@ -20,6 +20,17 @@
 namespace {
 
 const int kMaxChunks = 1024;
+const int kCounterInts = 32;   // [0] running total, [1] overflow; counter set q at 4 + 4q (q < 6)
+
+// One submission unit: windows [w0, w0 + nw) of the call.  `set` selects the buffer set and the
+// compute stream; `slot` is the chunk's first window slot inside that set, `xoff` its first
+// staged sample (host input), `cset` its private {coarse ticket, fine ticket, end} counters,
+// `group` the index of the full-size chunk it was cut from, `strm` its compute stream (the pieces
+// of a cut chunk alternate between the two streams so that they can overlap).
+struct UwChunk {
+    int w0, nw, set, slot, cset, group, strm;
+    size_t xoff;
+};
 
 struct Buffers {
     // per chunk
@@ -60,10 +71,13 @@ struct uwspr_b200_ctx {
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[2] = { nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int last_cw = 0;
+    std::vector<UwChunk> last_chunks;  // schedule of the last call
     int dev_chunks = 1;
     bool last_host = false;
     std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_cp0 = nullptr, ev_cp1 = nullptr, ev_kend = nullptr;  // UWSPR_B200_TRACE
+    bool trace = false;
     float ms[4] = { 0, 0, 0, 0 };
     int64_t launches = 0;
     std::string err;
@@ -263,7 +277,36 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     const int cw = host ? std::max(1, std::min(1024, ctx->chunk_windows / 2))
                         : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + ctx->dev_chunks - 1) / ctx->dev_chunks))
                                : ctx->chunk_windows);
-    const int nchunks = (nwin + cw - 1) / cw;
+    // Chunk schedule.  With host input the kernels of the last chunk cannot start before the last
+    // byte has crossed PCIe, so the final chunk is cut into 1/2, 1/4, 1/4, which use disjoint
+    // slices of that chunk's buffer set: the exposed tail is the compute time of a quarter chunk.
+    std::vector<UwChunk> &chunks = ctx->last_chunks;
+    chunks.clear();
+    {
+        int w = 0, group = 0;
+        while (nwin - w > cw) {
+            chunks.push_back(UwChunk{ w, cw, two ? (group & 1) : 0, 0, two ? (group & 1) : 0, group, two ? (group & 1) : 0, 0 });
+            w += cw;
+            group++;
+        }
+        const int rest = nwin - w, set = two ? (group & 1) : 0;
+        int parts[3] = { rest, 0, 0 };
+        if (host && group > 0 && rest >= 256 && !getenv("UWSPR_B200_NO_TAIL_SPLIT")) {
+            parts[0] = (rest + 1) / 2;
+            parts[1] = (rest - parts[0] + 1) / 2;
+            parts[2] = rest - parts[0] - parts[1];
+        }
+        int slot = 0;
+        size_t xoff = 0;
+        for (int q = 0; q < 3; q++) {
+            if (parts[q] <= 0) continue;
+            chunks.push_back(UwChunk{ w, parts[q], set, slot, q == 0 ? set : 1 + q, group, two ? ((set + q) & 1) : 0, xoff });
+            w += parts[q];
+            slot += parts[q];
+            xoff += (size_t)(parts[q] - 1) * (size_t)win_stride + (size_t)d.fl;
+        }
+    }
+    const int nchunks = (int)chunks.size();
     if (nchunks > kMaxChunks) return fail(ctx, UWSPR_B200_E_PARAM, "too many chunks: raise max_windows");
     while ((int)ctx->ev.size() < 4 * nchunks) {
         cudaEvent_t e;
@@ -272,7 +315,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     }
     cudaStream_t streams[2] = { cs, two && nchunks > 1 ? ctx->compute2 : cs };
     CU(cudaEventRecord(ctx->ev_begin, cs));
-    CU(cudaMemsetAsync(b.counters, 0, 16 * sizeof(int), cs));
+    CU(cudaMemsetAsync(b.counters, 0, kCounterInts * sizeof(int), cs));
     if (!do_coarse) {
         // candidate list comes from the caller (or stays from the previous coarse call)
         if (cands_in) {
@@ -291,33 +334,37 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     }
     const size_t span_max = (size_t)(cw - 1) * (size_t)win_stride + (size_t)d.fl;
     if (host) {
-        rc = ensure_stage(ctx, span_max);
+        rc = ensure_stage(ctx, span_max + 2 * (size_t)d.fl);  // cut chunks are staged back to back
         if (rc) return rc;
     }
     for (int c = 0; c < nchunks; c++) {
-        const int w0 = c * cw, nw = std::min(cw, nwin - w0);
-        const int s = two ? (c & 1) : 0;
-        cudaStream_t st = streams[s];
+        const UwChunk &ch = chunks[c];
+        const int w0 = ch.w0, nw = ch.nw, s = ch.set;
+        const bool first_of_group = c == 0 || chunks[c - 1].group != ch.group;
+        cudaStream_t st = streams[ch.strm];
         const float2 *xdev;
         if (host) {
-            // copy stream: wait until the kernels of chunk c-2 released this buffer set, then copy
-            if (c >= 2) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
+            // copy stream: wait until the kernels of the chunk two groups back released this buffer
+            // set, then copy
+            if (first_of_group && ch.group >= 2) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
+            if (ctx->trace && c == 0) CU(cudaEventRecord(ctx->ev_cp0, ctx->copy));
             const size_t span = (size_t)(nw - 1) * (size_t)win_stride + (size_t)d.fl;
-            CU(cudaMemcpyAsync(b.x_stage[s], samples + 2 * (size_t)w0 * (size_t)win_stride, span * sizeof(float2),
+            CU(cudaMemcpyAsync(b.x_stage[s] + ch.xoff, samples + 2 * (size_t)w0 * (size_t)win_stride, span * sizeof(float2),
                                cudaMemcpyHostToDevice, ctx->copy));
             CU(cudaEventRecord(ctx->ev_h2d[s], ctx->copy));
+            if (ctx->trace && c == nchunks - 1) CU(cudaEventRecord(ctx->ev_cp1, ctx->copy));
             CU(cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0));
-            xdev = b.x_stage[s];
+            xdev = b.x_stage[s] + ch.xoff;
         } else {
             xdev = reinterpret_cast<const float2 *>(samples) + (size_t)w0 * (size_t)win_stride;
         }
         // per-set slices of the chunk buffers
-        const size_t so = (size_t)s * cw;
+        const size_t so = (size_t)s * cw + (size_t)ch.slot;
         float *amp = b.amp + so * d.n_rows * d.nbp;
         float *psd = (ctx->debug_ps && b.ps_dbg) ? b.ps_dbg + so * d.n_rows * d.nbp : nullptr;
         float *psavg = b.psavg + so * d.nbp;
         UwPeak *peaks = b.peaks + so * d.maxcand;
-        int *set = b.counters + 4 + 4 * s;
+        int *set = b.counters + 4 + 4 * ch.cset;
         cudaEvent_t *e = &ctx->ev[4 * c];
         CU(cudaEventRecord(e[0], st));
         if (do_coarse) {
@@ -327,10 +374,10 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         }
         CU(cudaEventRecord(e[1], st));
         // the running total makes the work lists of consecutive chunks sequential
-        if (c >= 1 && streams[1] != cs) CU(cudaStreamWaitEvent(st, ctx->ev_wl[s ^ 1], 0));
+        if (c >= 1 && chunks[c - 1].strm != ch.strm) CU(cudaStreamWaitEvent(st, ctx->ev_wl[ch.strm ^ 1], 0));
         uw_launch_worklist(b.npk + w0, nw, ctx->max_candidates, b.base + w0, b.items, b.counters, set, st);
         ctx->launches++;
-        if (streams[1] != cs) CU(cudaEventRecord(ctx->ev_wl[s], st));
+        if (streams[1] != cs) CU(cudaEventRecord(ctx->ev_wl[ch.strm], st));
         if (do_coarse) {
             uw_launch_coarse(d, amp, peaks, b.items, set + 2, ctx->max_candidates, b.off4, b.hyp_unique, b.cands, set,
                              ctx->grid_coarse, st);
@@ -351,6 +398,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     }
     ctx->last_cw = cw;
     ctx->last_host = two;
+    if (ctx->trace) CU(cudaEventRecord(ctx->ev_kend, cs));
     int h_counters[4];
     CU(cudaMemcpyAsync(h_counters, b.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, cs));
     CU(cudaStreamSynchronize(cs));
@@ -384,6 +432,16 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         }
     }
     CU(cudaEventElapsedTime(&ctx->ms[3], ctx->ev_begin, ctx->ev_end));
+    if (ctx->trace) {
+        float k = 0.f, c0 = 0.f, c1 = 0.f;
+        cudaEventElapsedTime(&k, ctx->ev_begin, ctx->ev_kend);
+        if (host) {
+            cudaEventElapsedTime(&c0, ctx->ev_begin, ctx->ev_cp0);
+            cudaEventElapsedTime(&c1, ctx->ev_begin, ctx->ev_cp1);
+        }
+        fprintf(stderr, "uwspr_b200 trace: nwin %d chunks %d | first copy starts %.3f ms, last copy ends %.3f ms, "
+                        "kernels end %.3f ms, results on host %.3f ms\n", nwin, nchunks, c0, c1, k, ctx->ms[3]);
+    }
     ctx->have_coarse = true;
     ctx->last_nwin = nwin;
     ctx->last_total = total;
@@ -476,8 +534,8 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaMalloc(&b.refined, cap * sizeof(uwspr_b200_refined_t)));
     CUC(cudaMalloc(&b.jig, cap * UWSPR_B200_NJIG * sizeof(uwspr_b200_jiggle_t)));
     CUC(cudaMalloc(&b.soft, cap * UWSPR_B200_NJIG * UW_NSYM));
-    CUC(cudaMalloc(&b.counters, 16 * sizeof(int)));
-    CUC(cudaMemset(b.counters, 0, 16 * sizeof(int)));
+    CUC(cudaMalloc(&b.counters, kCounterInts * sizeof(int)));
+    CUC(cudaMemset(b.counters, 0, kCounterInts * sizeof(int)));
     // tables
     std::vector<float> window(UW_FFT_N);
     for (int i = 0; i < d.size; i++) window[i] = (float)sin((M_PI / (d.size - 1)) * i);  // FDR_impl.cc:103-105
@@ -505,6 +563,10 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
         CUC(cudaEventCreateWithFlags(&ctx->ev_wl[q], cudaEventDisableTiming));
     }
     CUC(cudaEventCreate(&ctx->ev_begin));
+    CUC(cudaEventCreate(&ctx->ev_cp0));
+    CUC(cudaEventCreate(&ctx->ev_cp1));
+    CUC(cudaEventCreate(&ctx->ev_kend));
+    ctx->trace = getenv("UWSPR_B200_TRACE") != nullptr;
     CUC(cudaEventCreate(&ctx->ev_end));
     if (uw_coarse_setup(d) || uw_fine_setup())
         return bail(fail(ctx, UWSPR_B200_E_CUDA, "cannot reserve shared memory for the kernels (not an sm_100a device?)"));
@@ -532,6 +594,9 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
         if (ctx->ev_wl[q]) cudaEventDestroy(ctx->ev_wl[q]);
     }
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_cp0) cudaEventDestroy(ctx->ev_cp0);
+    if (ctx->ev_cp1) cudaEventDestroy(ctx->ev_cp1);
+    if (ctx->ev_kend) cudaEventDestroy(ctx->ev_kend);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->compute && ctx->own_compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
@@ -633,11 +698,13 @@ int uwspr_b200_debug_spectrogram(uwspr_b200_ctx *ctx, int win, float *ps, float 
     if (!ctx->debug_ps || !ctx->b.ps_dbg) return fail(ctx, UWSPR_B200_E_STATE, "enable uwspr_b200_set_debug first");
     // the chunk buffers keep the last chunk (device input) or the last two (host input, two sets)
     const int cw = ctx->last_cw > 0 ? ctx->last_cw : 1;
-    const int nchunks = (ctx->last_nwin + cw - 1) / cw;
-    const int chunk = win / cw;
-    if (win < 0 || win >= ctx->last_nwin || chunk < nchunks - (ctx->last_host ? 2 : 1))
+    const std::vector<UwChunk> &chunks = ctx->last_chunks;
+    const UwChunk *ch = nullptr;
+    for (const UwChunk &q : chunks)
+        if (win >= q.w0 && win < q.w0 + q.nw) ch = &q;
+    if (win < 0 || win >= ctx->last_nwin || !ch || ch->group < chunks.back().group - (ctx->last_host ? 1 : 0))
         return fail(ctx, UWSPR_B200_E_PARAM, "window is not in the chunks still held on the device");
-    const size_t slot = (size_t)(ctx->last_host ? (chunk & 1) : 0) * cw + (size_t)(win - chunk * cw);
+    const size_t slot = (size_t)ch->set * cw + (size_t)ch->slot + (size_t)(win - ch->w0);
     CU(cudaSetDevice(ctx->device));
     const UwDims &d = ctx->d;
     std::vector<float> tmp((size_t)d.n_rows * d.nbp);

@@ -69,6 +69,7 @@ k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ pea
     short *hmap = reinterpret_cast<short *>(smem + L.map_off);
     __shared__ int s_item;
     __shared__ uint32_t s_sync[6];
+    __shared__ float s_gmax[UW_NIFR * UW_NK0];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int U = d.n_unique, S = L.tile_stride;
@@ -147,13 +148,26 @@ k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ pea
             sv[4 * UW_NK0 * U] = __fdiv_rn(ss4, pw4);
         }
         __syncthreads();
+        // largest sum of every (bin, shift) group (NaNs ignored), for the skip test of stage 3
+        if (tid < UW_NIFR * UW_NK0) {
+            const float *sv = syncv + tid * U;
+            float mx = -INFINITY;
+            for (int u = 0; u < U; u++) mx = fmaxf(mx, sv[u]);
+            s_gmax[tid] = mx;
+        }
+        __syncthreads();
 
         // stage 3: ordered replay of the update rule by warp 0
         if (tid < 32) {
             float cur = -1e30f;  // :340
             int b_type = -1, b_idx = 0, b_k0 = 0, b_a = 0;
+            // Once cur is positive and threshold >= 1, a group whose largest sum does not exceed cur
+            // cannot change anything: the linear rule needs v > cur, and v <= cur gives a correctly
+            // rounded v / cur <= 1 <= threshold.  Most of the 130 groups are skipped this way.
+            const bool can_skip = d.threshold >= 1.0f;
             for (int a = 0; a < UW_NIFR; a++) {
                 for (int k0 = 0; k0 < UW_NK0; k0++) {
+                    if (can_skip && cur > 0.0f && !(s_gmax[a * UW_NK0 + k0] > cur)) continue;
                     const float *sv = syncv + (a * UW_NK0 + k0) * U;
                     // linear drifts in order: running strict maximum == first maximum above cur
                     for (int base = 0; base < d.n_lin; base += 32) {
