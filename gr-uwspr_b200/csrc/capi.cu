@@ -66,7 +66,8 @@ struct uwspr_b200_ctx {
     int device = 0, sm_count = 0;
     int chunk_windows = 0, max_windows = 0, max_candidates = 0;
     int grid_coarse = 0, grid_fine = 0;
-    cudaStream_t compute = nullptr, compute2 = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, compute2 = nullptr, copy = nullptr, d2h = nullptr;
+    int *h_ends = nullptr;  // pinned: end of every chunk's items (host-fed calls stream results back per chunk)
     bool own_compute = true;
     cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[2] = { nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -337,6 +338,10 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         rc = ensure_stage(ctx, span_max + 2 * (size_t)d.fl);  // cut chunks are staged back to back
         if (rc) return rc;
     }
+    // Host-fed calls return results chunk by chunk while later chunks are still copying in and
+    // computing (PCIe is full duplex); only the last chunk's results are left for the end.
+    const bool want_results = (cands_out && do_coarse) || (do_fine && (refined_out || jig_out || soft_out));
+    const bool early = host && nchunks > 1 && want_results && !getenv("UWSPR_B200_NO_EARLY_D2H");
     for (int c = 0; c < nchunks; c++) {
         const UwChunk &ch = chunks[c];
         const int w0 = ch.w0, nw = ch.nw, s = ch.set;
@@ -378,6 +383,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         uw_launch_worklist(b.npk + w0, nw, ctx->max_candidates, b.base + w0, b.items, b.counters, set, st);
         ctx->launches++;
         if (streams[1] != cs) CU(cudaEventRecord(ctx->ev_wl[ch.strm], st));
+        if (early) CU(cudaMemcpyAsync(&ctx->h_ends[c], set + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (do_coarse) {
             uw_launch_coarse(d, amp, peaks, b.items, set + 2, ctx->max_candidates, b.off4, b.hyp_unique, b.cands, set,
                              ctx->grid_coarse, st);
@@ -399,9 +405,36 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     ctx->last_cw = cw;
     ctx->last_host = two;
     if (ctx->trace) CU(cudaEventRecord(ctx->ev_kend, cs));
+    int done = 0;  // results [0, done) are already on their way to the caller
+    auto fetch = [&](int lo, int hi, cudaStream_t q) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        const size_t n = (size_t)(hi - lo);
+        if (hi <= lo) return e;
+        if (cands_out && do_coarse && e == cudaSuccess)
+            e = cudaMemcpyAsync(cands_out + lo, b.cands + lo, sizeof(uwspr_b200_candidate_t) * n, cudaMemcpyDeviceToHost, q);
+        if (do_fine && refined_out && e == cudaSuccess)
+            e = cudaMemcpyAsync(refined_out + lo, b.refined + lo, sizeof(uwspr_b200_refined_t) * n, cudaMemcpyDeviceToHost, q);
+        if (do_fine && jig_out && e == cudaSuccess)
+            e = cudaMemcpyAsync(jig_out + (size_t)lo * jig_count, b.jig + (size_t)lo * jig_count,
+                                sizeof(uwspr_b200_jiggle_t) * n * jig_count, cudaMemcpyDeviceToHost, q);
+        if (do_fine && soft_out && e == cudaSuccess)
+            e = cudaMemcpyAsync(soft_out + (size_t)lo * jig_count * UW_NSYM, b.soft + (size_t)lo * jig_count * UW_NSYM,
+                                n * jig_count * UW_NSYM, cudaMemcpyDeviceToHost, q);
+        return e;
+    };
+    if (early) {
+        for (int c = 0; c + 1 < nchunks; c++) {
+            CU(cudaEventSynchronize(ctx->ev[4 * c + 3]));   // chunk c's kernels are done
+            const int end = ctx->h_ends[c];
+            if (end < done || (cands_out && do_coarse && end > cap_out)) break;  // capacity errors are reported below
+            CU(fetch(done, end, ctx->d2h));
+            done = end;
+        }
+    }
     int h_counters[4];
     CU(cudaMemcpyAsync(h_counters, b.counters, sizeof(h_counters), cudaMemcpyDeviceToHost, cs));
     CU(cudaStreamSynchronize(cs));
+    if (early) CU(cudaStreamSynchronize(ctx->d2h));  // nothing may still be writing caller memory if we fail below
     CU(cudaGetLastError());
     const int total = h_counters[0];
     if (h_counters[1]) return fail(ctx, UWSPR_B200_E_CAPACITY, "more candidates than max_candidates of the context");
@@ -412,16 +445,9 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         return fail(ctx, UWSPR_B200_E_PARAM, "sum of npk differs from total");
     }
     if (npk_out) CU(cudaMemcpyAsync(npk_out, b.npk, sizeof(int) * nwin, cudaMemcpyDeviceToHost, cs));
-    if (cands_out && total)
+    if (cands_out && !do_coarse && total)  // the caller's own list, echoed
         CU(cudaMemcpyAsync(cands_out, b.cands, sizeof(uwspr_b200_candidate_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
-    if (do_fine && total) {
-        if (refined_out)
-            CU(cudaMemcpyAsync(refined_out, b.refined, sizeof(uwspr_b200_refined_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
-        if (jig_out)
-            CU(cudaMemcpyAsync(jig_out, b.jig, sizeof(uwspr_b200_jiggle_t) * (size_t)total * jig_count, cudaMemcpyDeviceToHost, cs));
-        if (soft_out)
-            CU(cudaMemcpyAsync(soft_out, b.soft, (size_t)total * jig_count * UW_NSYM, cudaMemcpyDeviceToHost, cs));
-    }
+    CU(fetch(done, total, cs));
     CU(cudaEventRecord(ctx->ev_end, cs));
     CU(cudaStreamSynchronize(cs));
     for (int c = 0; c < nchunks; c++) {
@@ -555,6 +581,8 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+    CUC(cudaHostAlloc(&ctx->h_ends, sizeof(int) * (kMaxChunks + 4), cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     for (int q = 0; q < 2; q++) {
@@ -601,6 +629,8 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     if (ctx->compute && ctx->own_compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+    if (ctx->h_ends) cudaFreeHost(ctx->h_ends);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
