@@ -465,6 +465,14 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
             cudaEventElapsedTime(&c0, ctx->ev_begin, ctx->ev_cp0);
             cudaEventElapsedTime(&c1, ctx->ev_begin, ctx->ev_cp1);
         }
+        fprintf(stderr, "uwspr_b200 trace: chunk kernels start..end (ms):");
+        for (int c = 0; c < nchunks; c++) {
+            float a = 0.f, z = 0.f;
+            cudaEventElapsedTime(&a, ctx->ev_begin, ctx->ev[4 * c]);
+            cudaEventElapsedTime(&z, ctx->ev_begin, ctx->ev[4 * c + 3]);
+            fprintf(stderr, " [%d w%d] %.2f..%.2f", c, chunks[c].nw, a, z);
+        }
+        fprintf(stderr, "\n");
         fprintf(stderr, "uwspr_b200 trace: nwin %d chunks %d | first copy starts %.3f ms, last copy ends %.3f ms, "
                         "kernels end %.3f ms, results on host %.3f ms\n", nwin, nchunks, c0, c1, k, ctx->ms[3]);
     }

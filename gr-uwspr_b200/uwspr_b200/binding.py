@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
     "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack", "uwspr_b200_format_message_log",
+    "uwspr_b200_pack_type1", "uwspr_b200_channel_symbols",
 ]
 
 CAND_DTYPE = np.dtype(
@@ -96,6 +97,10 @@ def load_library():
     L.uwspr_b200_decode_candidate.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
     L.uwspr_b200_decode_batch.restype = C.c_int
     L.uwspr_b200_decode_batch.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.uwspr_b200_pack_type1.restype = C.c_int
+    L.uwspr_b200_pack_type1.argtypes = [C.c_char_p, C.c_char_p, C.c_int, vp]
+    L.uwspr_b200_channel_symbols.restype = None
+    L.uwspr_b200_channel_symbols.argtypes = [vp, vp]
     L.uwspr_b200_host_alloc.restype = C.c_int
     L.uwspr_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.uwspr_b200_host_free.argtypes = [vp]
@@ -389,6 +394,24 @@ class Receiver:
             self.close()
         except Exception:
             pass
+
+
+def pack_type1(call, grid, dbm):
+    """"CALL", "GRID", dBm -> the 7-byte type-1 message (what WSPR_unpacker turns back into text)"""
+    msg = np.zeros(7, np.int8)
+    st = load_library().uwspr_b200_pack_type1(call.encode(), grid.encode(), int(dbm), _p(msg))
+    if st != 0:
+        raise UwsprError(st, "not a type-1 message: %r %r %r" % (call, grid, dbm))
+    return msg.view(np.uint8)
+
+
+def channel_symbols(message7):
+    """7-byte message -> the 162 four-level channel symbols (0..3) a WSPR transmitter keys"""
+    msg = np.ascontiguousarray(message7).view(np.uint8)
+    assert msg.size == 7
+    out = np.zeros(162, np.uint8)
+    load_library().uwspr_b200_channel_symbols(_p(msg), _p(out))
+    return out
 
 
 def format_message_log(framecount, cand, message7):

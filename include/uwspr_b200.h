@@ -198,6 +198,14 @@ UWSPR_B200_API int uwspr_b200_decode_batch(const uwspr_b200_refined_t *refined,
 UWSPR_B200_API size_t uwspr_b200_hashtab_bytes(void);
 UWSPR_B200_API int uwspr_b200_unpack(const int8_t *message7, char *hashtab, char *text, size_t text_cap);
 
+/* Transmit direction, for synthetic inputs and tests (the reference ships only the receiver):
+ * "CALL", "GRID" (4 characters), dBm -> the 7-byte type-1 message uwspr_b200_unpack() reads back
+ * (inverse of lib/helpers.cc:321-434), and message -> the 162 four-level channel symbols
+ * (encoder lib/Fano.cc:81-100, interleaver inverse of sync_and_demodulate_impl.cc:265-282,
+ * symbol = 2*data + pr3[i]). */
+UWSPR_B200_API int uwspr_b200_pack_type1(const char *call, const char *grid4, int dbm, int8_t *message7);
+UWSPR_B200_API void uwspr_b200_channel_symbols(const int8_t *message7, uint8_t *symbols162);
+
 /* The text the reference appends to messagelog.txt for one decoded frame
  * (lib/sync_and_demodulate_impl.cc:508-525), without the two wall-clock lines before it. */
 UWSPR_B200_API int uwspr_b200_format_message_log(int framecount, const uwspr_b200_candidate_t *cand,

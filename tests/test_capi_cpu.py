@@ -197,3 +197,39 @@ def test_decode_batch_equals_candidate_loop_for_any_thread_count(lib):
         got = {g: (m.tobytes(), t) for g, m, t in ub.decode_candidates(refined, jig, soft, nthreads=nthreads)}
         assert got == want
     assert ub.decode_candidates(refined[:0], jig[:0], soft[:0]) == []
+
+
+def test_packer_and_channel_symbols_round_trip(lib, golden):
+    """transmit direction: text -> message -> channel symbols.  Known answers from the reference fixtures,
+    the encoder against the oracle's restatement of lib/Fano.cc, and text -> pack -> unpack == text with both
+    this library's unpacker and the compiled reference's"""
+    assert ub.pack_type1("VE3EMB", "FN25", 30).tobytes().hex() == "d42c73eb3a7780"
+    assert ub.pack_type1("ve3emb", "fn42", 33).tobytes().hex() == "d42c73eb0d1840"
+    assert np.array_equal(ub.channel_symbols(golden["kat/encode_in"][:7]), ob.channel_symbols(golden["kat/encode_in"][:7]))
+    rng = np.random.default_rng(3)
+    letters = "ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    u = ub.WSPR_unpacker()
+    try:
+        from oracle import ref_binding as rb
+        ru = rb.RefUnpacker() if os.path.exists("/root/reference") else None
+    except Exception:
+        ru = None
+    for trial in range(300):
+        n_suffix = int(rng.integers(1, 4))
+        if trial % 2:   # digit second: "K1ABC"
+            call = letters[rng.integers(26)] + str(rng.integers(10)) + "".join(letters[rng.integers(26)] for _ in range(n_suffix))
+        else:           # digit third: "VE3EMB"
+            call = letters[rng.integers(26)] + letters[rng.integers(26)] + str(rng.integers(10)) + \
+                "".join(letters[rng.integers(26)] for _ in range(n_suffix))
+        grid = letters[rng.integers(18)] + letters[rng.integers(18)] + str(rng.integers(10)) + str(rng.integers(10))
+        dbm = int(rng.choice([0, 3, 7, 10, 13, 17, 20, 23, 27, 30, 33, 37, 40, 43, 47, 50, 53, 57, 60]))
+        msg = ub.pack_type1(call, grid, dbm)
+        assert msg[6] & 0x3f == 0
+        want = "%s %s %2d" % (call, grid, dbm)   # the reference prints the power two wide
+        assert u.unpack(msg) == (0, want)
+        if ru is not None:
+            assert ru.unpack(msg)[1] == want
+        assert np.array_equal(ub.channel_symbols(msg), ob.channel_symbols(msg))
+    for bad in (("TOOLONGCALL", "FN25", 30), ("VE3EMB", "ZZ99", 30), ("VE3EMB", "FN25", 31), ("ABCDEF", "FN25", 30)):
+        with pytest.raises(ub.UwsprError):
+            ub.pack_type1(*bad)
