@@ -20,13 +20,14 @@
 namespace {
 
 const int kMaxChunks = 1024;
-const int kCounterInts = 32;   // [0] running total, [1] overflow; counter set q at 4 + 4q (q < 6)
+const int kCounterSets = 15;   // counter set q at 4 + 4q
+const int kCounterInts = 4 + 4 * kCounterSets;   // [0] running total, [1] overflow, then the sets
 
 // One submission unit: windows [w0, w0 + nw) of the call.  `set` selects the buffer set and the
 // compute stream; `slot` is the chunk's first window slot inside that set, `xoff` its first
 // staged sample (host input), `cset` its private {coarse ticket, fine ticket, end} counters,
 // `group` the index of the full-size chunk it was cut from, `strm` its compute stream (the pieces
-// of a cut chunk alternate between the two streams so that they can overlap).
+// of a cut chunk go to different streams so that they can overlap).
 struct UwChunk {
     int w0, nw, set, slot, cset, group, strm;
     size_t xoff;
@@ -66,11 +67,11 @@ struct uwspr_b200_ctx {
     int device = 0, sm_count = 0;
     int chunk_windows = 0, max_windows = 0, max_candidates = 0;
     int grid_coarse = 0, grid_fine = 0;
-    cudaStream_t compute = nullptr, compute2 = nullptr, copy = nullptr, d2h = nullptr;
+    cudaStream_t compute = nullptr, compute2 = nullptr, compute3 = nullptr, copy = nullptr, d2h = nullptr;
     int *h_ends = nullptr;  // pinned: end of every chunk's items (host-fed calls stream results back per chunk)
     bool own_compute = true;
-    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[2] = { nullptr, nullptr };
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int last_cw = 0;
     std::vector<UwChunk> last_chunks;  // schedule of the last call
     int dev_chunks = 1;
@@ -278,33 +279,42 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     const int cw = host ? std::max(1, std::min(1024, ctx->chunk_windows / 2))
                         : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + ctx->dev_chunks - 1) / ctx->dev_chunks))
                                : ctx->chunk_windows);
-    // Chunk schedule.  With host input the kernels of the last chunk cannot start before the last
-    // byte has crossed PCIe, so the final chunk is cut into 1/2, 1/4, 1/4, which use disjoint
-    // slices of that chunk's buffer set: the exposed tail is the compute time of a quarter chunk.
+    // Chunk schedule.  With host input the kernels of a chunk cannot start before its last byte
+    // has crossed PCIe, so the end of the call is cut into small pieces (a quarter chunk by
+    // default, UWSPR_B200_TAIL_PIECE) that use disjoint slices of their group's buffer set and
+    // rotate over three streams: when the last byte arrives only one small piece is left to do.
     std::vector<UwChunk> &chunks = ctx->last_chunks;
     chunks.clear();
     {
-        int w = 0, group = 0;
-        while (nwin - w > cw) {
-            chunks.push_back(UwChunk{ w, cw, two ? (group & 1) : 0, 0, two ? (group & 1) : 0, group, two ? (group & 1) : 0, 0 });
-            w += cw;
-            group++;
-        }
-        const int rest = nwin - w, set = two ? (group & 1) : 0;
-        int parts[3] = { rest, 0, 0 };
-        if (host && group > 0 && rest >= 256 && !getenv("UWSPR_B200_NO_TAIL_SPLIT")) {
-            parts[0] = (rest + 1) / 2;
-            parts[1] = (rest - parts[0] + 1) / 2;
-            parts[2] = rest - parts[0] - parts[1];
-        }
-        int slot = 0;
-        size_t xoff = 0;
-        for (int q = 0; q < 3; q++) {
-            if (parts[q] <= 0) continue;
-            chunks.push_back(UwChunk{ w, parts[q], set, slot, q == 0 ? set : 1 + q, group, two ? ((set + q) & 1) : 0, xoff });
-            w += parts[q];
-            slot += parts[q];
-            xoff += (size_t)(parts[q] - 1) * (size_t)win_stride + (size_t)d.fl;
+        int tail_groups = host ? 2 : 0, piece = std::max(1, cw / 4);
+        if (const char *e = getenv("UWSPR_B200_TAIL_GROUPS")) tail_groups = std::max(0, std::min(2, atoi(e)));
+        if (const char *e = getenv("UWSPR_B200_TAIL_PIECE")) piece = std::max(1, atoi(e));
+        if (!host || getenv("UWSPR_B200_NO_TAIL_SPLIT")) tail_groups = 0;
+        const int ngroups = (nwin + cw - 1) / cw;
+        int w = 0, cset = 2, rr = 0;
+        for (int group = 0; group < ngroups; group++) {
+            const int gw = std::min(cw, nwin - w), set = two ? (group & 1) : 0;
+            const bool cut = group > 0 && group >= ngroups - tail_groups && gw > piece;
+            if (!cut) {
+                chunks.push_back(UwChunk{ w, gw, set, 0, set, group, set, 0 });
+                w += gw;
+                continue;
+            }
+            int slot = 0;
+            size_t xoff = 0;
+            while (slot < gw) {
+                // a last piece shorter than half a piece is merged into its predecessor
+                int pw = std::min(piece, gw - slot);
+                if (gw - slot - pw < (piece + 1) / 2) pw = gw - slot;
+                const bool spare = cset < kCounterSets;
+                chunks.push_back(UwChunk{ w, spare ? pw : gw - slot, set, slot, spare ? cset : set, group, rr % 3, xoff });
+                if (!spare) pw = gw - slot;
+                else cset++;
+                rr++;
+                w += pw;
+                slot += pw;
+                xoff += (size_t)(pw - 1) * (size_t)win_stride + (size_t)d.fl;
+            }
         }
     }
     const int nchunks = (int)chunks.size();
@@ -314,7 +324,9 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         CU(cudaEventCreate(&e));
         ctx->ev.push_back(e);
     }
-    cudaStream_t streams[2] = { cs, two && nchunks > 1 ? ctx->compute2 : cs };
+    cudaStream_t streams[3] = { cs, two && nchunks > 1 ? ctx->compute2 : cs, ctx->compute3 };
+    bool use3 = false;
+    for (const UwChunk &q : chunks) use3 = use3 || q.strm == 2;
     CU(cudaEventRecord(ctx->ev_begin, cs));
     CU(cudaMemsetAsync(b.counters, 0, kCounterInts * sizeof(int), cs));
     if (!do_coarse) {
@@ -332,10 +344,11 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     if (streams[1] != cs) {
         CU(cudaEventRecord(ctx->ev_fork, cs));
         CU(cudaStreamWaitEvent(streams[1], ctx->ev_fork, 0));
+        if (use3) CU(cudaStreamWaitEvent(streams[2], ctx->ev_fork, 0));
     }
     const size_t span_max = (size_t)(cw - 1) * (size_t)win_stride + (size_t)d.fl;
     if (host) {
-        rc = ensure_stage(ctx, span_max + 2 * (size_t)d.fl);  // cut chunks are staged back to back
+        rc = ensure_stage(ctx, span_max + (size_t)kCounterSets * (size_t)d.fl);  // pieces of a cut chunk are staged back to back
         if (rc) return rc;
     }
     // Host-fed calls return results chunk by chunk while later chunks are still copying in and
@@ -379,7 +392,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         }
         CU(cudaEventRecord(e[1], st));
         // the running total makes the work lists of consecutive chunks sequential
-        if (c >= 1 && chunks[c - 1].strm != ch.strm) CU(cudaStreamWaitEvent(st, ctx->ev_wl[ch.strm ^ 1], 0));
+        if (c >= 1 && chunks[c - 1].strm != ch.strm) CU(cudaStreamWaitEvent(st, ctx->ev_wl[chunks[c - 1].strm], 0));
         uw_launch_worklist(b.npk + w0, nw, ctx->max_candidates, b.base + w0, b.items, b.counters, set, st);
         ctx->launches++;
         if (streams[1] != cs) CU(cudaEventRecord(ctx->ev_wl[ch.strm], st));
@@ -401,6 +414,10 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     if (streams[1] != cs) {
         CU(cudaEventRecord(ctx->ev_join, streams[1]));
         CU(cudaStreamWaitEvent(cs, ctx->ev_join, 0));
+        if (use3) {
+            CU(cudaEventRecord(ctx->ev_join3, streams[2]));
+            CU(cudaStreamWaitEvent(cs, ctx->ev_join3, 0));
+        }
     }
     ctx->last_cw = cw;
     ctx->last_host = two;
@@ -590,6 +607,9 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->compute3, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_wl[2], cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
     CUC(cudaHostAlloc(&ctx->h_ends, sizeof(int) * (kMaxChunks + 4), cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -638,6 +658,9 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
     if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+    if (ctx->compute3) cudaStreamDestroy(ctx->compute3);
+    if (ctx->ev_wl[2]) cudaEventDestroy(ctx->ev_wl[2]);
+    if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
     if (ctx->h_ends) cudaFreeHost(ctx->h_ends);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

@@ -18,7 +18,8 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
     "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack", "uwspr_b200_format_message_log",
-    "uwspr_b200_pack_type1", "uwspr_b200_channel_symbols",
+    "uwspr_b200_pack_type1", "uwspr_b200_channel_symbols", "uwspr_b200_read_c2", "uwspr_b200_frontend",
+    "uwspr_b200_frontend_error",
 ]
 
 CAND_DTYPE = np.dtype(
@@ -101,6 +102,12 @@ def load_library():
     L.uwspr_b200_pack_type1.argtypes = [C.c_char_p, C.c_char_p, C.c_int, vp]
     L.uwspr_b200_channel_symbols.restype = None
     L.uwspr_b200_channel_symbols.argtypes = [vp, vp]
+    L.uwspr_b200_read_c2.restype = C.c_int
+    L.uwspr_b200_read_c2.argtypes = [C.c_char_p, vp, vp, vp, vp]
+    L.uwspr_b200_frontend.restype = C.c_int
+    L.uwspr_b200_frontend.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, vp, C.c_int, C.c_int,
+                                      C.c_int, C.c_double, C.c_double, vp, C.c_int, C.c_int64, vp]
+    L.uwspr_b200_frontend_error.restype = C.c_char_p
     L.uwspr_b200_host_alloc.restype = C.c_int
     L.uwspr_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.uwspr_b200_host_free.argtypes = [vp]
@@ -394,6 +401,60 @@ class Receiver:
             self.close()
         except Exception:
             pass
+
+
+def read_c2(path):
+    """uwspr.c2file_source's reader: (complex64[45000] = I - jQ, name, type, dial frequency in MHz)"""
+    iq = np.zeros(45000, np.complex64)
+    name = C.create_string_buffer(15)
+    typ, freq = C.c_int32(), C.c_double()
+    st = load_library().uwspr_b200_read_c2(os.fsencode(path), _p(iq), name, C.byref(typ), C.byref(freq))
+    if st != 0:
+        raise UwsprError(st, "cannot read 45000 samples from %r" % (path,))
+    return iq, name.value.decode("latin1"), typ.value, freq.value
+
+
+def lowpass_taps(ntaps=513, cutoff=150.0, fs_in=12000.0):
+    """Hamming-windowed sinc low-pass with unit DC gain (what gnuradio.filter.firdes.low_pass designs)"""
+    k = np.arange(ntaps) - (ntaps - 1) / 2
+    h = np.sinc(2 * cutoff / fs_in * k) * np.hamming(ntaps)
+    return (h / h.sum()).astype(np.float32)
+
+
+def frontend(audio, taps=None, decim=32, fc=1500.0, fs_in=12000.0, delay=None, device=0, out_device_ptr=None,
+             out_stride=None):
+    """real audio [nchan, n] or [n] (float32, or int16 PCM) at fs_in -> complex64 at fs_in/decim on the GPU
+    (uwspr_b200_frontend).  `audio` may be a numpy array or a (device pointer, dtype, shape) tuple; the result is a
+    numpy array, or stays on the device when out_device_ptr is given.  delay defaults to the filter's group delay."""
+    L = load_library()
+    taps = lowpass_taps(fs_in=fs_in) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
+    delay = (len(taps) - 1) // 2 if delay is None else int(delay)
+    if isinstance(audio, tuple):
+        ptr, dtype, shape = audio
+        space_in = 1
+    else:
+        a = np.ascontiguousarray(audio)
+        if a.dtype != np.int16:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+        ptr, dtype, shape, space_in = _p(a), a.dtype, a.shape, 0
+    fmt = 1 if np.dtype(dtype) == np.int16 else 0
+    nchan, n_in = (1, shape[0]) if len(shape) == 1 else shape
+    n_out = n_in // decim
+    stride = n_out if out_stride is None else int(out_stride)
+    got = C.c_int64()
+    if out_device_ptr is None:
+        out = np.zeros((nchan, stride), np.complex64)
+        optr, space_out = _p(out), 0
+    else:
+        out, optr, space_out = None, C.c_void_p(int(out_device_ptr)), 1
+    st = L.uwspr_b200_frontend(device, ptr, fmt, space_in, n_in, nchan, n_in, _p(taps), len(taps), decim, delay, fc, fs_in,
+                               optr, space_out, stride, C.byref(got))
+    if st != 0:
+        raise UwsprError(st, L.uwspr_b200_frontend_error().decode())
+    if out is None:
+        return got.value
+    out = out[:, :got.value]
+    return out[0] if len(shape) == 1 else out
 
 
 def pack_type1(call, grid, dbm):

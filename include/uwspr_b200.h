@@ -206,6 +206,27 @@ UWSPR_B200_API int uwspr_b200_unpack(const int8_t *message7, char *hashtab, char
 UWSPR_B200_API int uwspr_b200_pack_type1(const char *call, const char *grid4, int dbm, int8_t *message7);
 UWSPR_B200_API void uwspr_b200_channel_symbols(const int8_t *message7, uint8_t *symbols162);
 
+/* ---- upstream of the path ---------------------------------------------------------------
+ * uwspr.c2file_source's reader (lib/c2file_source_impl.cc:75-96): 45000 complex samples at
+ * 375 sps as I - jQ (the reference flips the quadrature sign at :91) into iq[2*45000];
+ * name15 (15 bytes), type and freq_mhz may be NULL.  E_PARAM if the file cannot be read or is short. */
+UWSPR_B200_API int uwspr_b200_read_c2(const char *path, float *iq, char *name15, int32_t *type, double *freq_mhz);
+
+/* Front-end on the device (stock GNU Radio blocks in the reference's flowgraphs,
+ * examples/WaveFilePlusNoiseDecode.grc:834-958,1753-1810): real audio -> mix down by fc ->
+ * FIR -> keep every decim-th sample:
+ *     y[m] = sum_k taps[k] * x[n-k] * exp(-2 pi i fc (n-k) / fs_in),  n = m*decim + delay,
+ * x = 0 outside [0, n_in).  audio: nchan channels of n_in samples, chan_stride apart, fmt 0 =
+ * float32, 1 = int16 (scaled by 1/32768 like blocks_wavfile_source); out: complex64, channel c at
+ * out + 2*c*out_stride floats, *n_out = n_in / decim samples each.  space_in / space_out say
+ * where the buffers live; a device output feeds uwspr_b200_coarse_fine directly. */
+UWSPR_B200_API int uwspr_b200_frontend(int device, const void *audio, int fmt, int space_in,
+                                       int64_t chan_stride, int nchan, int64_t n_in,
+                                       const float *taps, int ntaps, int decim, int delay, double fc,
+                                       double fs_in, float *out, int space_out, int64_t out_stride,
+                                       int64_t *n_out);
+UWSPR_B200_API const char *uwspr_b200_frontend_error(void);
+
 /* The text the reference appends to messagelog.txt for one decoded frame
  * (lib/sync_and_demodulate_impl.cc:508-525), without the two wall-clock lines before it. */
 UWSPR_B200_API int uwspr_b200_format_message_log(int framecount, const uwspr_b200_candidate_t *cand,

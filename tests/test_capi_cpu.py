@@ -233,3 +233,24 @@ def test_packer_and_channel_symbols_round_trip(lib, golden):
     for bad in (("TOOLONGCALL", "FN25", 30), ("VE3EMB", "ZZ99", 30), ("VE3EMB", "FN25", 31), ("ABCDEF", "FN25", 30)):
         with pytest.raises(ub.UwsprError):
             ub.pack_type1(*bad)
+
+
+def test_c2_reader(lib, golden_windows, tmp_path):
+    """uwspr.c2file_source's reader: header fields, conjugation on load (c2file_source_impl.cc:91), short files refused"""
+    import struct
+    x = golden_windows["ve3emb_c2"]
+    raw = np.empty((45000, 2), "<f4")
+    raw[:, 0], raw[:, 1] = x.real, -x.imag     # what the file holds: the reader flips the sign back
+    path = tmp_path / "t.c2"
+    path.write_bytes(struct.pack("<14sid", b"150426_0918.c2", 2, 10.1387) + raw.tobytes())
+    iq, name, typ, freq = ub.read_c2(str(path))
+    assert (name, typ, freq) == ("150426_0918.c2", 2, 10.1387)
+    assert iq.tobytes() == x.tobytes()
+    (tmp_path / "short.c2").write_bytes(path.read_bytes()[:-8])
+    with pytest.raises(ub.UwsprError):
+        ub.read_c2(str(tmp_path / "short.c2"))
+    with pytest.raises(ub.UwsprError):
+        ub.read_c2(str(tmp_path / "missing.c2"))
+    ref = "/root/reference/examples/VE3EMB.c2"
+    if os.path.exists(ref):
+        assert ub.read_c2(ref)[0].tobytes() == x.tobytes()

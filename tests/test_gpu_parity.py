@@ -422,3 +422,99 @@ def test_hydrophone_array_with_whale_noise():
             g = base[i] + msgs[j][0]
             assert abs(int(refined["shift1"][g]) - (metas[w]["start"] + int(metas[w]["delays"][c]))) <= 48
     assert heard.mean() > 0.7
+
+
+def test_frontend_audio_to_messages():
+    """12 kHz real audio -> GPU front-end (mix down 1500 Hz, FIR, keep every 32nd) -> 375-sps complex that stays on
+    the device -> coarse + fine -> host decoder -> unpacker: the transmitted texts come back.  The front-end itself
+    is checked against a float64 evaluation of the same formula (no GNU Radio here to pin its stock blocks)."""
+    import torch
+    from scipy.signal import fftconvolve
+    texts = [("VE3EMB", "FN25", 30), ("K1ABC", "FN42", 37)]
+    fs_in, decim, n_in = 12000.0, 32, 45000 * 32
+    rng = np.random.default_rng(12)
+    t = np.arange(n_in) / fs_in
+    audio = np.zeros((2, n_in))
+    for c, (call, grid, dbm) in enumerate(texts):
+        sym = ub.channel_symbols(ub.pack_type1(call, grid, dbm)).astype(np.float64)
+        # 4-FSK at audio: tone (sym - 1.5) * 375/256 Hz around 1500 + f0, 8192 audio samples per symbol
+        f0 = (-3.3, 4.1)[c]
+        start = int((1.0 + 0.37 * c) * fs_in)
+        f = 1500.0 + f0 + (np.repeat(sym, 8192) - 1.5) * 375.0 / 256.0
+        ph = 2 * np.pi * np.cumsum(f) / fs_in
+        audio[c, start:start + 162 * 8192] = 0.2 * np.cos(ph)
+        audio[c] += 0.05 * rng.standard_normal(n_in)
+    taps = ub.lowpass_taps()
+    # float64 oracle of the documented formula
+    k = (len(taps) - 1) // 2
+    want = np.empty((2, n_in // decim), np.complex128)
+    for c in range(2):
+        bb = audio[c] * np.exp(-2j * np.pi * 1500.0 * np.arange(n_in) / fs_in)
+        full = fftconvolve(bb, taps.astype(np.float64))[k:][:n_in]
+        want[c] = full[::decim]
+    got = ub.frontend(audio.astype(np.float32), taps=taps)
+    scale = np.sqrt((np.abs(want) ** 2).mean())
+    assert got.shape == want.shape and np.abs(got - want).max() < 2e-5 * scale * 10
+    pcm = np.clip(np.round(audio * 32768.0), -32768, 32767).astype(np.int16)
+    got16 = ub.frontend(pcm, taps=taps)
+    want16 = np.empty_like(want)
+    for c in range(2):
+        bb = (pcm[c] / 32768.0) * np.exp(-2j * np.pi * 1500.0 * np.arange(n_in) / fs_in)
+        want16[c] = fftconvolve(bb, taps.astype(np.float64))[k:][:n_in][::decim]
+    assert np.abs(got16 - want16).max() < 2e-4 * scale
+    # device to device: audio and the 375-sps stream never leave the GPU
+    a_dev = torch.from_numpy(audio.astype(np.float32)).cuda()
+    x_dev = torch.empty((2, 45000, 2), dtype=torch.float32, device="cuda")
+    import ctypes
+    n_out = ub.frontend((ctypes.c_void_p(a_dev.data_ptr()), np.float32, tuple(a_dev.shape)), taps=taps,
+                        out_device_ptr=x_dev.data_ptr())
+    assert n_out == 45000
+    torch.cuda.synchronize()
+    assert np.array_equal(x_dev.cpu().numpy().view(np.complex64)[..., 0], got)
+    ctx = ctx_for(maxdrift=0, max_windows=2)
+    npk, cands, refined, jig, soft = ctx.coarse_fine((x_dev.data_ptr(), 2 * 45000), nwin=2, stride=45000)
+    u = ub.WSPR_unpacker()
+    base = np.concatenate([[0], np.cumsum(npk)])
+    for c, (call, grid, dbm) in enumerate(texts):
+        sl = slice(base[c], base[c + 1])
+        heard = {u.unpack(m)[1] for _, m, _ in ub.decode_candidates(refined[sl], jig[sl], soft[sl])}
+        assert "%s %s %2d" % (call, grid, dbm) in heard
+    # and the same windows through the oracle chain decode to the same blobs
+    of = ob.OracleFDR(maxdrift=0)
+    for c in range(2):
+        oc = of.transform(got[c])
+        blobs, _, _ = ob.demodulate(got[c], oc)
+        sl = slice(base[c], base[c + 1])
+        mine = [bytes(m) for _, m, _ in ub.decode_candidates(refined[sl], jig[sl], soft[sl])]
+        assert mine == [bytes(b) for b in blobs]
+
+
+@pytest.mark.parametrize("piece,groups,stride", [(3, 2, 45000), (1, 2, 22500), (5, 1, 45000), (2, 2, 3375)])
+def test_host_fed_tail_pieces(piece, groups, stride, monkeypatch):
+    """host-fed calls cut their last chunk groups into small pieces on three streams and return results chunk by
+    chunk; with tiny piece sizes every path of that schedule runs on a 21-window call, and the results must equal
+    the single-submission ones byte for byte (independent and overlapping windows)"""
+    nwin = 21
+    n = 45000 + (nwin - 1) * stride
+    rng = np.random.default_rng(99)
+    stream = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.5).astype(np.complex64)
+    for k, start in enumerate(range(2000, n - 162 * 256, 60000)):
+        msg = td.message_bytes(np.random.default_rng(k))
+        stream[start:start + 162 * 256] += td.modulate(ob.channel_symbols(msg), f0=-5.0 + 1.7 * (k % 6), drift=0.0, start=0,
+                                                       fl=162 * 256).astype(np.complex64)
+    big = ctx_for(max_windows=64)
+    import torch
+    t = torch.from_numpy(stream.view(np.float32)).cuda()
+    want = big.coarse_fine((t.data_ptr(), stream.size), nwin=nwin, stride=stride)     # one chunk, device input
+    monkeypatch.setenv("UWSPR_B200_TAIL_PIECE", str(piece))
+    monkeypatch.setenv("UWSPR_B200_TAIL_GROUPS", str(groups))
+    small = ub.Context(max_windows=21, max_candidates=21 * 14)   # host chunk groups of 10, 10 and 1 windows
+    got = small.coarse_fine(stream, nwin=nwin, stride=stride)
+    assert want[0].sum() >= 3
+    for u, v in zip(want, got):
+        assert u.tobytes() == v.tobytes()
+    out = small.result_buffers(nwin)
+    got2 = small.coarse_fine(stream, nwin=nwin, stride=stride, out=out)
+    for u, v in zip(want, got2):
+        assert u.tobytes() == np.asarray(v).tobytes()
+    small.close()
