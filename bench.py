@@ -266,7 +266,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import uwspr_b200 as ub
-    from uwspr_b200.sharding import gather_counts
+    from uwspr_b200.sharding import balanced_counts, gather_counts, gather_floats
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -284,7 +284,13 @@ def run_ours(args):
     nfr = args.windows
     stride = FL // 2 if args.overlap else FL
     nwin = 2 * nfr - 1 if args.overlap else nfr
-    ctx = ub.Context(device=local, max_windows=nwin, max_candidates=max(4 * nwin, 1024), **PARAMS)
+    # Host-fed arm at N > 1: the box's host links are not equally fast when every GPU copies at once (pairs of
+    # GPUs share a PCIe uplink, half of them sit behind a socket hop), so the N x nwin windows of a step are
+    # split over the ranks in proportion to each rank's measured host-fed rate instead of equally; a rank
+    # therefore keeps up to 1.5 x nwin windows on the host.  The device-resident arm stays at nwin per GPU.
+    balance = world > 1 and not args.overlap and not args.no_balance
+    nmax = int(1.5 * nwin) if balance else nwin
+    ctx = ub.Context(device=local, max_windows=nmax, max_candidates=max(4 * nmax, 1024), **PARAMS)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
@@ -294,8 +300,13 @@ def run_ours(args):
     xs_dev, truth = gen_windows_torch(nfr, seed=rank, device=dev)
     dptr = (xs_dev.data_ptr(), nfr * FL)
     # pinned host copy for the end-to-end arm
-    xs_host_t = torch.empty((nfr, FL), dtype=torch.complex64, pin_memory=True)
-    xs_host_t.copy_(xs_dev)
+    xs_host_t = torch.empty((nmax if balance else nfr, FL), dtype=torch.complex64, pin_memory=True)
+    xs_host_t[:nfr].copy_(xs_dev)
+    if balance and nmax > nfr:
+        extra, truth_extra = gen_windows_torch(nmax - nfr, seed=1000 + rank, device=dev)
+        xs_host_t[nfr:].copy_(extra)
+        truth = list(truth) + list(truth_extra)
+        del extra
     torch.cuda.synchronize(dev)
     xs_host = xs_host_t.numpy()
 
@@ -329,10 +340,11 @@ def run_ours(args):
 
     e2e_out = {}
 
-    out_bufs = ctx.result_buffers(nwin)   # pinned, allocated once (as a streaming caller would)
+    out_bufs = ctx.result_buffers(nmax)   # pinned, allocated once (as a streaming caller would)
+    n_e2e = [nwin]                        # this rank's windows per host-fed step
 
     def step_e2e():
-        e2e_out["r"] = ctx.coarse_fine(xs_host.reshape(-1), nwin=nwin, stride=stride, out=out_bufs)
+        e2e_out["r"] = ctx.coarse_fine(xs_host.reshape(-1), nwin=n_e2e[0], stride=stride, out=out_bufs)
 
     for _ in range(args.warmup):
         step_dev()
@@ -346,6 +358,18 @@ def run_ours(args):
     ncand = totals[-1]
     for _ in range(min(args.warmup, 1) or 1):
         step_e2e()
+    e2e_counts = [nwin] * world
+    if balance:
+        # three rounds: the rates seen under an equal split are already those of full contention for the
+        # fast links; the later rounds correct the slow ones (they sped up once the fast ranks had finished)
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            step_e2e()
+            torch.cuda.synchronize(dev)
+            rates = gather_floats(n_e2e[0] / (time.perf_counter() - t0), dist)
+            e2e_counts = balanced_counts(world * nwin, rates, lo=max(1, nwin // 4), hi=nmax)
+            n_e2e[0] = e2e_counts[rank]
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
     npk, cands, refined, jig, soft = e2e_out["r"]
@@ -353,13 +377,14 @@ def run_ours(args):
     # context for the end-to-end number: the plain pinned-host -> device copy rate of this box
     scratch = torch.empty_like(xs_dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scratch.copy_(xs_host_t, non_blocking=True)
-    torch.cuda.synchronize(dev)
+    scratch.copy_(xs_host_t[:nfr], non_blocking=True)
+    barrier()   # every rank copies at the same time, as in the host-fed steps
     ev0.record(stream)
-    scratch.copy_(xs_host_t, non_blocking=True)
+    scratch.copy_(xs_host_t[:nfr], non_blocking=True)
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     pcie_gbs = h2d / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    pcie_all = gather_floats(pcie_gbs, dist if world > 1 else None)
     del scratch
     d2h = npk.nbytes + cands.nbytes + refined.nbytes + jig.nbytes + soft.nbytes
 
@@ -404,7 +429,11 @@ def run_ours(args):
                     jiggles="all 17 per gated candidate", host_numa_node=numa, candidates=ncand, gated=gated, sync_evaluations=evals,
                     **{k: PARAMS[k] for k in ("maxdrift", "halfbandwidth", "threshold", "maxfreqs")}),
         e2e=dict(value=e2e_value, unit="windows/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=int(d2h), ms_per_step=ms_e2e / args.steps,
-                 pcie_h2d_gbs=pcie_gbs, pcie_bound_windows_per_s=world * pcie_gbs * 1e9 / (h2d / nwin)),
+                 pcie_h2d_gbs=pcie_gbs, pcie_h2d_gbs_per_rank=[round(v, 2) for v in pcie_all],
+                 pcie_bound_windows_per_s=sum(pcie_all) * 1e9 / (h2d / nwin),
+                 windows_per_rank=e2e_counts,
+                 split=("windows split over the ranks in proportion to each rank's measured host-fed rate "
+                        "(uwspr_b200.sharding.balanced_counts); same total as the equal split" if balance else "equal")),
         gpu_launches=int(launches),
         stage_ms=dict(spectrogram_normalizer=float(st[0]), coarse_search=float(st[1]), fine_sync_demod=fine_ms, call=float(st[3])),
         roofline=dict(bound="hbm", kernel="k_fine (fine sync + soft symbols)", achieved=alg_bytes / (fine_ms * 1e-3) / 1e9, peak=hbm_peak,
@@ -418,7 +447,7 @@ def run_ours(args):
                                 "ceiling is one mul OR add per lane per clock: 148 SM x 128 lanes x 1.965 GHz = 37.2 T/s "
                                 "(tools/fp32_pipes.cu measures 34.7-35.8); the FMA peak (74.4) is not reachable without "
                                 "changing results"),
-        decoded=dict(messages=len(dec), correct=int(good), windows=nwin, frames=nfr),
+        decoded=dict(messages=len(dec), correct=int(good), windows=int(len(npk)), frames=nfr),
         clocks=clocks, cpu_baseline=cpu,
     )
     print(json.dumps(line))
@@ -441,6 +470,7 @@ def main():
     ap.add_argument("--windows", type=int, default=10000, help="windows per GPU")
     ap.add_argument("--ref-windows-per-core", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="host-fed arm at N > 1: equal split instead of link-rate balanced")
     ap.add_argument("--overlap", action="store_true", help="windows every 22 500 samples of one stream (not the default workload)")
     args = ap.parse_args()
     if args.impl == "reference":

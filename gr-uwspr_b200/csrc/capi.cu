@@ -276,7 +276,9 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     // sets/streams so that one chunk's spectrogram/coarse kernels fill idle issue slots of the
     // previous chunk's fine kernel
     const bool two = host || ctx->dev_chunks > 1;
-    const int cw = host ? std::max(1, std::min(1024, ctx->chunk_windows / 2))
+    int host_chunk = 1024;  // tuning knob
+    if (const char *e = getenv("UWSPR_B200_HOST_CHUNK")) host_chunk = std::max(1, atoi(e));
+    const int cw = host ? std::max(1, std::min(host_chunk, ctx->chunk_windows / 2))
                         : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + ctx->dev_chunks - 1) / ctx->dev_chunks))
                                : ctx->chunk_windows);
     // Chunk schedule.  With host input the kernels of a chunk cannot start before its last byte
