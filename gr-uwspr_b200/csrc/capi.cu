@@ -522,10 +522,7 @@ const char *uwspr_b200_status_string(int status)
 
 const char *uwspr_b200_last_error(const uwspr_b200_ctx *ctx)
 {
-    static const char *none = "";
-    static std::string create_err;
-    (void)create_err;
-    return ctx ? ctx->err.c_str() : none;
+    return ctx ? ctx->err.c_str() : "";
 }
 
 static std::string g_create_error;
