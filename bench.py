@@ -18,6 +18,11 @@ the metric on both sides).
 
 With N > 1 (torchrun) each rank runs the same per-GPU workload on its own GPU (weak scaling,
 no data-path collective); time is the max over ranks, value the sum of windows / that time.
+The host-fed arm (e2e) at N > 1 processes the same N x M windows per step but deals them to
+the ranks in proportion to each rank's measured host-fed rate, because the host links of one
+box are not equally fast when every GPU copies at once (--no-balance: equal split).
+The synthetic inputs are made with the library's own encoder (uwspr_b200.channel_symbols);
+oracle/ is used by the reference arm and the cpu_baseline leg only.
 --impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified
 sources; the C restatement if it was not built) on all host cores, on a bounded sample.
 """
@@ -47,25 +52,34 @@ FLOP_SPEC, FLOP_COARSE, FLOP_POINT = 9.09e6, 5 * 26 * (2 * PARAMS["maxdrift"] + 
 
 
 # ------------------------------------------------------------------ synthetic windows
+SEED_BASE = 20190222
+
+
+def message_bytes(rng):
+    """50 random payload bits packed MSB-first into 7 bytes (last 6 bits zero)"""
+    b = np.zeros(56, np.uint8)
+    b[:50] = rng.integers(0, 2, 50, dtype=np.uint8)
+    return np.packbits(b)
+
+
 def gen_windows_torch(nwin, seed, device, maxdrift=3.0, batch=500):
     """synthetic windows of SURVEY 8(d) generated on the GPU (torch is plumbing here: the data
     generator is not part of the measured path).  Returns a (nwin, FL) complex64 CUDA tensor
     and the per-window truth."""
     import torch
-    from oracle import port_binding as ob
-    from oracle import testdata as td
-    rng = np.random.default_rng([td.SEED_BASE, seed])
+    import uwspr_b200 as ub   # the library's own encoder: nothing under oracle/ feeds the measured arms
+    rng = np.random.default_rng([SEED_BASE, seed])
     out = torch.empty((nwin, FL), dtype=torch.complex64, device=device)
     gen = torch.Generator(device=device)
-    gen.manual_seed(td.SEED_BASE + 7919 * seed)
+    gen.manual_seed(SEED_BASE + 7919 * seed)
     truth = []
     df = 375.0 / 256.0
     k = torch.arange(162 * 256, device=device)
     sym_idx = (k // 256)
     for b0 in range(0, nwin, batch):
         nb = min(batch, nwin - b0)
-        msgs = [td.message_bytes(rng) for _ in range(nb)]
-        syms = np.stack([ob.channel_symbols(m) for m in msgs]).astype(np.float64)
+        msgs = [message_bytes(rng) for _ in range(nb)]
+        syms = np.stack([ub.channel_symbols(m) for m in msgs]).astype(np.float64)
         f0 = rng.uniform(-6, 6, nb)
         drift = rng.uniform(-maxdrift, maxdrift, nb)
         start = 375 + rng.integers(0, 2561, nb)
