@@ -517,4 +517,10 @@ def test_host_fed_tail_pieces(piece, groups, stride, monkeypatch):
     got2 = small.coarse_fine(stream, nwin=nwin, stride=stride, out=out)
     for u, v in zip(want, got2):
         assert u.tobytes() == np.asarray(v).tobytes()
+    # the two block-level calls on their own, chunked the same way: coarse, then fine with the caller's list
+    npk, cands = small.coarse(stream, nwin=nwin, stride=stride)
+    assert npk.tobytes() == want[0].tobytes() and cands.tobytes() == want[1].tobytes()
+    fine = small.fine(stream, npk, cands, nwin=nwin, stride=stride)
+    for u, v in zip(want[2:], fine):
+        assert u.tobytes() == v.tobytes()
     small.close()
