@@ -439,7 +439,7 @@ def frontend(audio, taps=None, decim=32, fc=1500.0, fs_in=12000.0, delay=None, d
         ptr, dtype, shape, space_in = _p(a), a.dtype, a.shape, 0
     fmt = 1 if np.dtype(dtype) == np.int16 else 0
     nchan, n_in = (1, shape[0]) if len(shape) == 1 else shape
-    n_out = n_in // decim
+    n_out = n_in // decim if decim > 0 else 0   # the library reports the bad argument
     stride = n_out if out_stride is None else int(out_stride)
     got = C.c_int64()
     if out_device_ptr is None:

@@ -254,3 +254,29 @@ def test_c2_reader(lib, golden_windows, tmp_path):
     ref = "/root/reference/examples/VE3EMB.c2"
     if os.path.exists(ref):
         assert ub.read_c2(ref)[0].tobytes() == x.tobytes()
+
+
+def test_frontend_and_batch_decoder_argument_checks(lib):
+    """argument errors are statuses, reported before any CUDA call (so they can be checked without a GPU)"""
+    audio = np.zeros(64, np.float32)
+    taps = np.ones(4, np.float32)
+    with pytest.raises(ub.UwsprError):
+        ub.frontend(audio, taps=np.zeros(0, np.float32))          # no taps
+    with pytest.raises(ub.UwsprError):
+        ub.frontend(audio, taps=taps, decim=0)                     # bad decimation
+    with pytest.raises(ub.UwsprError):
+        ub.frontend(audio, taps=taps, fs_in=0.0)                   # bad rate
+    with pytest.raises(ub.UwsprError):
+        ub.frontend(audio, taps=taps, delay=-1)
+    L = lib
+    r = np.zeros(1, ub.REFINED_DTYPE)
+    j = np.zeros((1, 17), ub.JIG_DTYPE)
+    s = np.zeros((1, 17, 162), np.uint8)
+    d = np.zeros(1, np.uint8)
+    m = np.zeros(7, np.int8)
+    P = ub.binding._p
+    assert L.uwspr_b200_decode_batch(P(r), P(j), P(s), 1, 18, 0, P(d), P(m), None, None) < 0     # jig_count > 17
+    assert L.uwspr_b200_decode_batch(P(r), P(j), P(s), -1, 17, 0, P(d), P(m), None, None) < 0
+    assert L.uwspr_b200_decode_batch(None, None, None, 0, 17, 0, None, None, None, None) == 0   # nothing to do
+    assert L.uwspr_b200_decode_batch(P(r), P(j), P(s), 1, 17, 0, None, P(m), None, None) < 0     # no output
+    assert L.uwspr_b200_decode_batch(P(r), P(j), P(s), 1, 17, 2, P(d), P(m), None, None) == 0 and d[0] == 0
