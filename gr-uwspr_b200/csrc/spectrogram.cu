@@ -178,6 +178,8 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             float *dbg_row = ps_dbg ? ps_dbg + ((long long)win * d.n_rows + row) * d.nbp : nullptr;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
+                // narrow bands keep exactly one output per thread (r = 0 or r = 7): skip the other tests
+                if ((keep == 0x01u && r != 0) || (keep == 0x80u && r != 7)) continue;
                 const int kbin = j + 64 * r;                 // FFT bin (0 = DC)
                 const int sh = (kbin + UW_FFT_N / 2) & (UW_FFT_N - 1);  // index after the shift of :247-248
                 const int c = sh - d.bin_lo;
