@@ -33,6 +33,41 @@ struct UwChunk {
     size_t xoff;
 };
 
+// Tuning / diagnosis knobs, read from the environment once, when the context is created
+// (DESIGN.md section 3 lists them).
+struct Knobs {
+    int host_chunk = 1024;      // UWSPR_B200_HOST_CHUNK: windows per host-fed chunk
+    int tail_groups = 2;        // UWSPR_B200_TAIL_GROUPS: chunk groups at the end of a host-fed call that are cut up
+    int tail_piece = 0;         // UWSPR_B200_TAIL_PIECE: windows per piece (0: a quarter chunk)
+    bool no_tail_split = false; // UWSPR_B200_NO_TAIL_SPLIT
+    bool no_early_d2h = false;  // UWSPR_B200_NO_EARLY_D2H
+    bool trace = false;         // UWSPR_B200_TRACE
+    int dev_chunks = 1;         // UWSPR_B200_DEV_CHUNKS
+    int stagger_fine_us = 0;    // UWSPR_B200_STAGGER_FINE_US / _COARSE_US: start offset between the CTAs that share an SM
+    int stagger_coarse_us = 0;
+    int fine_ctas_per_sm = 0;   // UWSPR_B200_FINE_CTAS_PER_SM: fewer resident CTAs than fit (occupancy experiments)
+};
+
+Knobs read_knobs()
+{
+    Knobs k;
+    auto geti = [](const char *name, int def) {
+        const char *e = getenv(name);
+        return e ? atoi(e) : def;
+    };
+    k.host_chunk = std::max(1, geti("UWSPR_B200_HOST_CHUNK", k.host_chunk));
+    k.tail_groups = std::max(0, std::min(2, geti("UWSPR_B200_TAIL_GROUPS", k.tail_groups)));
+    k.tail_piece = std::max(0, geti("UWSPR_B200_TAIL_PIECE", 0));
+    k.no_tail_split = getenv("UWSPR_B200_NO_TAIL_SPLIT") != nullptr;
+    k.no_early_d2h = getenv("UWSPR_B200_NO_EARLY_D2H") != nullptr;
+    k.trace = getenv("UWSPR_B200_TRACE") != nullptr;
+    k.dev_chunks = std::max(1, geti("UWSPR_B200_DEV_CHUNKS", 1));
+    k.stagger_fine_us = std::max(0, geti("UWSPR_B200_STAGGER_FINE_US", 0));
+    k.stagger_coarse_us = std::max(0, geti("UWSPR_B200_STAGGER_COARSE_US", 0));
+    k.fine_ctas_per_sm = std::max(0, geti("UWSPR_B200_FINE_CTAS_PER_SM", 0));
+    return k;
+}
+
 struct Buffers {
     // per chunk
     float2 *x_stage[2] = { nullptr, nullptr };  // host-fed samples, double buffered
@@ -50,6 +85,7 @@ struct Buffers {
     uwspr_b200_refined_t *refined = nullptr;
     uwspr_b200_jiggle_t *jig = nullptr;
     uint8_t *soft = nullptr;
+    int *sm_slots = nullptr;  // 2 x 256 arrival counters per SM (uw_stagger)
     int *counters = nullptr;  // [0] running total, [1] overflow; set s at 4+4s: ticket coarse, ticket fine, end of chunk
     // tables
     float *window = nullptr;
@@ -74,12 +110,11 @@ struct uwspr_b200_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int last_cw = 0;
     std::vector<UwChunk> last_chunks;  // schedule of the last call
-    int dev_chunks = 1;
+    Knobs knobs;
     bool last_host = false;
     std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t ev_cp0 = nullptr, ev_cp1 = nullptr, ev_kend = nullptr;  // UWSPR_B200_TRACE
-    bool trace = false;
     float ms[4] = { 0, 0, 0, 0 };
     int64_t launches = 0;
     std::string err;
@@ -275,11 +310,10 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     // dev_chunks > 1 (tuning knob, UWSPR_B200_DEV_CHUNKS): device input is also split over the two
     // sets/streams so that one chunk's spectrogram/coarse kernels fill idle issue slots of the
     // previous chunk's fine kernel
-    const bool two = host || ctx->dev_chunks > 1;
-    int host_chunk = 1024;  // tuning knob
-    if (const char *e = getenv("UWSPR_B200_HOST_CHUNK")) host_chunk = std::max(1, atoi(e));
-    const int cw = host ? std::max(1, std::min(host_chunk, ctx->chunk_windows / 2))
-                        : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + ctx->dev_chunks - 1) / ctx->dev_chunks))
+    const Knobs &kn = ctx->knobs;
+    const bool two = host || kn.dev_chunks > 1;
+    const int cw = host ? std::max(1, std::min(kn.host_chunk, ctx->chunk_windows / 2))
+                        : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + kn.dev_chunks - 1) / kn.dev_chunks))
                                : ctx->chunk_windows);
     // Chunk schedule.  With host input the kernels of a chunk cannot start before its last byte
     // has crossed PCIe, so the end of the call is cut into small pieces (a quarter chunk by
@@ -288,10 +322,9 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     std::vector<UwChunk> &chunks = ctx->last_chunks;
     chunks.clear();
     {
-        int tail_groups = host ? 2 : 0, piece = std::max(1, cw / 4);
-        if (const char *e = getenv("UWSPR_B200_TAIL_GROUPS")) tail_groups = std::max(0, std::min(2, atoi(e)));
-        if (const char *e = getenv("UWSPR_B200_TAIL_PIECE")) piece = std::max(1, atoi(e));
-        if (!host || getenv("UWSPR_B200_NO_TAIL_SPLIT")) tail_groups = 0;
+        int tail_groups = host ? kn.tail_groups : 0;
+        const int piece = kn.tail_piece > 0 ? kn.tail_piece : std::max(1, cw / 4);
+        if (!host || kn.no_tail_split) tail_groups = 0;
         const int ngroups = (nwin + cw - 1) / cw;
         int w = 0, cset = 2, rr = 0;
         for (int group = 0; group < ngroups; group++) {
@@ -356,7 +389,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     // Host-fed calls return results chunk by chunk while later chunks are still copying in and
     // computing (PCIe is full duplex); only the last chunk's results are left for the end.
     const bool want_results = (cands_out && do_coarse) || (do_fine && (refined_out || jig_out || soft_out));
-    const bool early = host && nchunks > 1 && want_results && !getenv("UWSPR_B200_NO_EARLY_D2H");
+    const bool early = host && nchunks > 1 && want_results && !kn.no_early_d2h;
     for (int c = 0; c < nchunks; c++) {
         const UwChunk &ch = chunks[c];
         const int w0 = ch.w0, nw = ch.nw, s = ch.set;
@@ -367,12 +400,12 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
             // copy stream: wait until the kernels of the chunk two groups back released this buffer
             // set, then copy
             if (first_of_group && ch.group >= 2) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
-            if (ctx->trace && c == 0) CU(cudaEventRecord(ctx->ev_cp0, ctx->copy));
+            if (ctx->knobs.trace && c == 0) CU(cudaEventRecord(ctx->ev_cp0, ctx->copy));
             const size_t span = (size_t)(nw - 1) * (size_t)win_stride + (size_t)d.fl;
             CU(cudaMemcpyAsync(b.x_stage[s] + ch.xoff, samples + 2 * (size_t)w0 * (size_t)win_stride, span * sizeof(float2),
                                cudaMemcpyHostToDevice, ctx->copy));
             CU(cudaEventRecord(ctx->ev_h2d[s], ctx->copy));
-            if (ctx->trace && c == nchunks - 1) CU(cudaEventRecord(ctx->ev_cp1, ctx->copy));
+            if (ctx->knobs.trace && c == nchunks - 1) CU(cudaEventRecord(ctx->ev_cp1, ctx->copy));
             CU(cudaStreamWaitEvent(st, ctx->ev_h2d[s], 0));
             xdev = b.x_stage[s] + ch.xoff;
         } else {
@@ -401,13 +434,13 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         if (early) CU(cudaMemcpyAsync(&ctx->h_ends[c], set + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (do_coarse) {
             uw_launch_coarse(d, amp, peaks, b.items, set + 2, ctx->max_candidates, b.off4, b.hyp_unique, b.cands, set,
-                             ctx->grid_coarse, st);
+                             ctx->grid_coarse, kn.stagger_coarse_us, ctx->grid_coarse / ctx->sm_count, b.sm_slots, st);
             ctx->launches++;
         }
         CU(cudaEventRecord(e[2], st));
         if (do_fine) {
             uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 2, ctx->max_candidates, b.cands, jig_first,
-                           jig_count, b.refined, b.jig, b.soft, set + 1, ctx->grid_fine, st);
+                           jig_count, b.refined, b.jig, b.soft, set + 1, ctx->grid_fine, kn.stagger_fine_us, ctx->grid_fine / ctx->sm_count, b.sm_slots + 256, st);
             ctx->launches++;
         }
         CU(cudaEventRecord(e[3], st));
@@ -423,7 +456,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     }
     ctx->last_cw = cw;
     ctx->last_host = two;
-    if (ctx->trace) CU(cudaEventRecord(ctx->ev_kend, cs));
+    if (ctx->knobs.trace) CU(cudaEventRecord(ctx->ev_kend, cs));
     int done = 0;  // results [0, done) are already on their way to the caller
     auto fetch = [&](int lo, int hi, cudaStream_t q) -> cudaError_t {
         cudaError_t e = cudaSuccess;
@@ -477,7 +510,7 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         }
     }
     CU(cudaEventElapsedTime(&ctx->ms[3], ctx->ev_begin, ctx->ev_end));
-    if (ctx->trace) {
+    if (ctx->knobs.trace) {
         float k = 0.f, c0 = 0.f, c1 = 0.f;
         cudaEventElapsedTime(&k, ctx->ev_begin, ctx->ev_kend);
         if (host) {
@@ -571,7 +604,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     UwDims &d = ctx->d;
     ctx->max_windows = p.max_windows > 0 ? p.max_windows : 1;
     ctx->chunk_windows = std::min(ctx->max_windows, 16384);
-    if (const char *e = getenv("UWSPR_B200_DEV_CHUNKS")) ctx->dev_chunks = std::max(1, atoi(e));
+    ctx->knobs = read_knobs();
     const long long def_cap = (long long)ctx->max_windows * d.maxcand;
     ctx->max_candidates = p.max_candidates > 0 ? p.max_candidates : (int)std::min<long long>(def_cap, 1 << 22);
     Buffers &b = ctx->b;
@@ -586,6 +619,8 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaMalloc(&b.soft, cap * UWSPR_B200_NJIG * UW_NSYM));
     CUC(cudaMalloc(&b.counters, kCounterInts * sizeof(int)));
     CUC(cudaMemset(b.counters, 0, kCounterInts * sizeof(int)));
+    CUC(cudaMalloc(&b.sm_slots, 512 * sizeof(int)));
+    CUC(cudaMemset(b.sm_slots, 0, 512 * sizeof(int)));
     // tables
     std::vector<float> window(UW_FFT_N);
     for (int i = 0; i < d.size; i++) window[i] = (float)sin((M_PI / (d.size - 1)) * i);  // FDR_impl.cc:103-105
@@ -621,12 +656,12 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaEventCreate(&ctx->ev_cp0));
     CUC(cudaEventCreate(&ctx->ev_cp1));
     CUC(cudaEventCreate(&ctx->ev_kend));
-    ctx->trace = getenv("UWSPR_B200_TRACE") != nullptr;
     CUC(cudaEventCreate(&ctx->ev_end));
     if (uw_coarse_setup(d) || uw_fine_setup())
         return bail(fail(ctx, UWSPR_B200_E_CUDA, "cannot reserve shared memory for the kernels (not an sm_100a device?)"));
     ctx->grid_coarse = ctx->sm_count * uw_coarse_blocks_per_sm(d);
     ctx->grid_fine = ctx->sm_count * uw_fine_blocks_per_sm();
+    if (ctx->knobs.fine_ctas_per_sm > 0) ctx->grid_fine = ctx->sm_count * std::min(ctx->knobs.fine_ctas_per_sm, uw_fine_blocks_per_sm());
     CUC(cudaDeviceSynchronize());
 #undef CUC
     *ctx_out = ctx;
@@ -639,7 +674,7 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
     void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
-                     b.cands, b.refined, b.jig, b.soft, b.counters, b.window, b.twiddle, b.off4, b.hyp_unique };
+                     b.cands, b.refined, b.jig, b.soft, b.counters, b.sm_slots, b.window, b.twiddle, b.off4, b.hyp_unique };
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kThreads)
 k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ peaks,
          const UwItem *__restrict__ items, const int *__restrict__ total_ptr, int cap,
          const uint32_t *__restrict__ off4_g, const short *__restrict__ hyp_unique_g,
-         uwspr_b200_candidate_t *__restrict__ cands, int *__restrict__ ticket)
+         uwspr_b200_candidate_t *__restrict__ cands, int *__restrict__ ticket, int stagger_us, int ctas_per_sm, int *__restrict__ slots)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const CoarseLayout L = coarse_layout(d.n_rows, d.tile_w, d.n_unique, d.n_hyp);
@@ -75,6 +75,7 @@ k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ pea
     const int U = d.n_unique, S = L.tile_stride;
     const int total = min(*total_ptr, cap);
 
+    uw_stagger(stagger_us, ctas_per_sm, slots);
     for (int t = tid; t < UW_NQUAD * U; t += kThreads) off4[t] = off4_g[t];
     for (int t = tid; t < d.n_hyp; t += kThreads) hmap[t] = hyp_unique_g[t];
     if (tid == 0) {
@@ -259,10 +260,10 @@ int uw_coarse_setup(const UwDims &d)
 
 void uw_launch_coarse(const UwDims &d, const float *amp, const UwPeak *peaks, const UwItem *items,
                       const int *total, int cap, const uint32_t *off4, const short *hyp_unique,
-                      uwspr_b200_candidate_t *cands, int *ticket, int grid, cudaStream_t s)
+                      uwspr_b200_candidate_t *cands, int *ticket, int grid, int stagger_us, int ctas_per_sm, int *slots, cudaStream_t s)
 {
     k_coarse<<<grid, kThreads, uw_coarse_smem_bytes(d), s>>>(d, amp, peaks, items, total, cap, off4,
-                                                             hyp_unique, cands, ticket);
+                                                             hyp_unique, cands, ticket, stagger_us, ctas_per_sm, slots);
 }
 
 int uw_coarse_blocks_per_sm(const UwDims &d)

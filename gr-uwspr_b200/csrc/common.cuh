@@ -50,6 +50,84 @@ __device__ __forceinline__ int uw_sync_bit(const uint32_t *words, int i)
     return (int)((words[i >> 5] >> (i & 31)) & 1u);
 }
 
+// Start offset between the CTAs that share an SM.  Every candidate costs nearly the same, so
+// co-resident CTAs of a persistent grid that start together stay in the same phase of their stage
+// sequence for the whole launch and their sparse phases (stage tails, single-warp replays) coincide; a
+// one-off offset of a fraction of a candidate's duration keeps them apart.  `slots` holds one counter
+// per SM (never reset: arrival order modulo the CTAs per SM is all that matters).
+__device__ __forceinline__ void uw_stagger(int us_per_class, int ctas_per_sm, int *slots)
+{
+    if (us_per_class <= 0) return;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int cls = atomicAdd(&slots[smid & 255], 1) % ctas_per_sm;
+        if (cls > 0) {
+            unsigned long long t0, t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            const unsigned long long wait_ns = (unsigned long long)cls * (unsigned long long)us_per_class * 1000ull;
+            do {
+                __nanosleep(2000);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            } while (t - t0 < wait_ns);
+        }
+    }
+    __syncthreads();
+}
+
+// ---- packed fp32 pairs (sm_100a: add/sub/fma.rn.f32x2 -> FADD2 / FFMA2) ------------------
+// One issue slot carries two independent IEEE round-to-nearest operations, each bit-identical
+// to its scalar form.  The kernels that mirror reference sums are bound by issue slots and
+// the fp32 pipe (no FMA contraction allowed), so they pair two accumulation chains that
+// share an operand (two tones against one sample, two bins against one shift).
+// ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 even under
+// --fmad=false, which would round once instead of twice.  The product is therefore issued
+// as fma(a, b, -0.0) with the -0.0 pair in a kernel parameter (opaque to ptxas):
+// a*b + (-0) is a*b rounded once, sign of zero included, and an FFMA2 cannot be merged
+// with the addition that consumes it.
+typedef unsigned long long uw_f2;
+#define UW_NEGZERO2 0x8000000080000000ull
+
+__device__ __forceinline__ uw_f2 uw_pk(float lo, float hi)
+{
+    uw_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float uw_lo(uw_f2 v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float uw_hi(uw_f2 v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ uw_f2 uw_add2(uw_f2 a, uw_f2 b)
+{
+    uw_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uw_f2 uw_sub2(uw_f2 a, uw_f2 b)
+{
+    uw_f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// both products rounded once each; nz must be UW_NEGZERO2 read from a kernel parameter
+__device__ __forceinline__ uw_f2 uw_mul2(uw_f2 a, uw_f2 b, uw_f2 nz)
+{
+    uw_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+// scalar times pair (the scalar is broadcast by the instruction's operand form)
+__device__ __forceinline__ uw_f2 uw_mul2s(float a, uw_f2 b, uw_f2 nz) { return uw_mul2(uw_pk(a, a), b, nz); }
+
 // launches (defined in the .cu files)
 void uw_launch_spectrogram(const UwDims &d, const float2 *x, long long win_stride, int nwin,
                            const float *window, const float2 *twiddle, float *amp, float *ps_dbg,
@@ -58,11 +136,11 @@ void uw_launch_worklist(const int *npk, int nwin, int cap, int *base, UwItem *it
                         int *set, cudaStream_t s);
 void uw_launch_coarse(const UwDims &d, const float *amp, const UwPeak *peaks, const UwItem *items,
                       const int *total, int cap, const uint32_t *off4, const short *hyp_unique,
-                      uwspr_b200_candidate_t *cands, int *ticket, int grid, cudaStream_t s);
+                      uwspr_b200_candidate_t *cands, int *ticket, int grid, int stagger_us, int ctas_per_sm, int *slots, cudaStream_t s);
 void uw_launch_fine(const UwDims &d, const float2 *x, long long win_stride, const UwItem *items,
                     const int *total, int cap, const uwspr_b200_candidate_t *cands, int jig_first,
                     int jig_count, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig,
-                    uint8_t *soft, int *ticket, int grid, cudaStream_t s);
+                    uint8_t *soft, int *ticket, int grid, int stagger_us, int ctas_per_sm, int *slots, cudaStream_t s);
 size_t uw_coarse_smem_bytes(const UwDims &d);
 size_t uw_fine_smem_bytes();
 int uw_coarse_setup(const UwDims &d);
