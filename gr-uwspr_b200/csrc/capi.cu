@@ -7,7 +7,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <future>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -123,6 +126,7 @@ struct uwspr_b200_ctx {
     int last_nwin = 0, last_total = 0;
     const float *last_samples = nullptr;
     int64_t last_stride = 0;
+    std::future<int> pending;   // uwspr_b200_coarse_fine_submit: the submission running on its own thread
 };
 
 namespace {
@@ -254,6 +258,7 @@ int ensure_window_capacity(uwspr_b200_ctx *ctx, int nwin)
     if (b.base) cudaFree(b.base);
     b.npk = nullptr;
     b.base = nullptr;
+    b.win_cap = 0;
     const size_t n = (size_t)nwin + 1;
     CU(cudaMalloc(&b.npk, n * sizeof(int)));
     CU(cudaMalloc(&b.base, n * sizeof(int)));
@@ -279,10 +284,10 @@ int ensure_stage(uwspr_b200_ctx *ctx, size_t elems)
 //   do_coarse: spectrogram + normalizer + peaks + coarse search -> device candidate list
 //   do_fine:   refinement + soft symbols for the device candidate list
 // When !do_coarse the candidate list (npk + cands) is uploaded from the caller first.
-int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin, bool do_coarse,
-        bool do_fine, const int32_t *npk_in, const uwspr_b200_candidate_t *cands_in, int total_in, int jig_first,
-        int jig_count, int32_t *npk_out, uwspr_b200_candidate_t *cands_out, int cap_out, int32_t *total_out,
-        uwspr_b200_refined_t *refined_out, uwspr_b200_jiggle_t *jig_out, uint8_t *soft_out)
+int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin, bool do_coarse,
+             bool do_fine, const int32_t *npk_in, const uwspr_b200_candidate_t *cands_in, int total_in, int jig_first,
+             int jig_count, int32_t *npk_out, uwspr_b200_candidate_t *cands_out, int cap_out, int32_t *total_out,
+             uwspr_b200_refined_t *refined_out, uwspr_b200_jiggle_t *jig_out, uint8_t *soft_out)
 {
     if (!ctx) return UWSPR_B200_E_PARAM;
     if (nwin < 0 || !samples || win_stride < 0) return fail(ctx, UWSPR_B200_E_PARAM, "bad sample arguments");
@@ -368,7 +373,14 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
         // candidate list comes from the caller (or stays from the previous coarse call)
         if (cands_in) {
             if (!npk_in) return fail(ctx, UWSPR_B200_E_PARAM, "cands given without npk");
+            if (total_in < 0) return fail(ctx, UWSPR_B200_E_PARAM, "negative candidate total");
             if (total_in > ctx->max_candidates) return fail(ctx, UWSPR_B200_E_CAPACITY, "more candidates than max_candidates");
+            long long sum = 0;
+            for (int w = 0; w < nwin; w++) {
+                if (npk_in[w] < 0) return fail(ctx, UWSPR_B200_E_PARAM, "negative candidate count for a window");
+                sum += npk_in[w];
+            }
+            if (sum != total_in) return fail(ctx, UWSPR_B200_E_PARAM, "sum of npk differs from total");
             CU(cudaMemcpyAsync(b.npk, npk_in, sizeof(int) * nwin, cudaMemcpyHostToDevice, cs));
             CU(cudaMemcpyAsync(b.cands, cands_in, sizeof(uwspr_b200_candidate_t) * (size_t)total_in,
                                cudaMemcpyHostToDevice, cs));
@@ -536,6 +548,27 @@ int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride
     return UWSPR_B200_OK;
 }
 
+// Every failure leaves through here: nothing may still be copying into the caller's buffers or running on
+// the context's streams once an error status has been returned, and a candidate list left by a call that
+// failed half way must not be used by a following fine(cands == NULL).
+int run(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin, bool do_coarse,
+        bool do_fine, const int32_t *npk_in, const uwspr_b200_candidate_t *cands_in, int total_in, int jig_first,
+        int jig_count, int32_t *npk_out, uwspr_b200_candidate_t *cands_out, int cap_out, int32_t *total_out,
+        uwspr_b200_refined_t *refined_out, uwspr_b200_jiggle_t *jig_out, uint8_t *soft_out)
+{
+    const int rc = run_impl(ctx, samples, space, win_stride, nwin, do_coarse, do_fine, npk_in, cands_in, total_in, jig_first,
+                            jig_count, npk_out, cands_out, cap_out, total_out, refined_out, jig_out, soft_out);
+    if (rc != UWSPR_B200_OK && ctx) {
+        cudaStream_t all[5] = { ctx->compute, ctx->compute2, ctx->compute3, ctx->copy, ctx->d2h };
+        for (cudaStream_t q : all)
+            if (q) cudaStreamSynchronize(q);
+        cudaGetLastError();
+        ctx->have_coarse = false;
+        ctx->last_nwin = 0;
+    }
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -558,7 +591,7 @@ const char *uwspr_b200_last_error(const uwspr_b200_ctx *ctx)
     return ctx ? ctx->err.c_str() : "";
 }
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // per thread: contexts may be created concurrently
 UWSPR_B200_API const char *uwspr_b200_create_error(void) { return g_create_error.c_str(); }
 
 int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_out)
@@ -671,6 +704,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
 void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->pending.valid()) ctx->pending.wait();
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
     void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
@@ -724,9 +758,15 @@ int uwspr_b200_info(const uwspr_b200_ctx *ctx, uwspr_b200_info_t *info)
     return UWSPR_B200_OK;
 }
 
+static int busy(uwspr_b200_ctx *ctx)
+{
+    return (ctx && ctx->pending.valid()) ? fail(ctx, UWSPR_B200_E_STATE, "a submitted call has not been waited for (uwspr_b200_wait)") : 0;
+}
+
 int uwspr_b200_coarse(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin,
                       int32_t *npk, uwspr_b200_candidate_t *cands, int cap, int32_t *total)
 {
+    if (busy(ctx)) return UWSPR_B200_E_STATE;
     return run(ctx, samples, space, win_stride, nwin, true, false, nullptr, nullptr, 0, 0, 0, npk, cands, cap, total,
                nullptr, nullptr, nullptr);
 }
@@ -735,6 +775,7 @@ int uwspr_b200_fine(uwspr_b200_ctx *ctx, const float *samples, int space, int64_
                     const int32_t *npk, const uwspr_b200_candidate_t *cands, int total, int jig_first,
                     int jig_count, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft)
 {
+    if (busy(ctx)) return UWSPR_B200_E_STATE;
     return run(ctx, samples, space, win_stride, nwin, false, true, npk, cands, total, jig_first, jig_count, nullptr,
                nullptr, 0, nullptr, refined, jig, soft);
 }
@@ -743,8 +784,40 @@ int uwspr_b200_coarse_fine(uwspr_b200_ctx *ctx, const float *samples, int space,
                            int jig_first, int jig_count, int32_t *npk, uwspr_b200_candidate_t *cands, int cap,
                            int32_t *total, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft)
 {
+    if (busy(ctx)) return UWSPR_B200_E_STATE;
     return run(ctx, samples, space, win_stride, nwin, true, true, nullptr, nullptr, 0, jig_first, jig_count, npk, cands,
                cap, total, refined, jig, soft);
+}
+
+int uwspr_b200_coarse_fine_submit(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_stride, int nwin,
+                                  int jig_first, int jig_count, int32_t *npk, uwspr_b200_candidate_t *cands, int cap,
+                                  int32_t *total, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft)
+{
+    if (!ctx) return UWSPR_B200_E_PARAM;
+    if (ctx->pending.valid()) return fail(ctx, UWSPR_B200_E_STATE, "one submission at a time per context: wait for the previous one");
+    // run() drives copies and kernels with stream waits and a few event synchronisations of its own; on its own
+    // thread none of them blocks the caller (a GNU Radio message handler returns at once and picks the results up later)
+    std::packaged_task<int()> task([=]() {
+        return run(ctx, samples, space, win_stride, nwin, true, true, nullptr, nullptr, 0, jig_first, jig_count, npk, cands, cap,
+                   total, refined, jig, soft);
+    });
+    std::future<int> fut = task.get_future();
+    std::thread(std::move(task)).detach();
+    ctx->pending = std::move(fut);   // the worker thread never touches `pending`; the synchronous entry points check it
+    return UWSPR_B200_OK;
+}
+
+int uwspr_b200_poll(uwspr_b200_ctx *ctx)
+{
+    if (!ctx || !ctx->pending.valid()) return -1;
+    return ctx->pending.wait_for(std::chrono::seconds(0)) == std::future_status::ready ? 1 : 0;
+}
+
+int uwspr_b200_wait(uwspr_b200_ctx *ctx)
+{
+    if (!ctx) return UWSPR_B200_E_PARAM;
+    if (!ctx->pending.valid()) return fail(ctx, UWSPR_B200_E_STATE, "nothing was submitted");
+    return ctx->pending.get();
 }
 
 int uwspr_b200_host_alloc(void **ptr, size_t bytes)

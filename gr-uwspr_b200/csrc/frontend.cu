@@ -104,6 +104,7 @@ extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int s
     if (!audio || !taps || !out || nchan < 1 || n_in < 1 || ntaps < 1 || ntaps > 16384 || decim < 1 || decim > 4096 ||
         delay < 0 || !(fs_in > 0.0) || (fmt != 0 && fmt != 1) || chan_stride < n_in)
         return fe_fail(UWSPR_B200_E_PARAM, "bad front-end arguments");
+    if (nchan > 65535) return fe_fail(UWSPR_B200_E_PARAM, "more than 65535 channels in one call (grid.y limit)");
     const int64_t n_out = n_in / decim;
     if (n_out_p) *n_out_p = n_out;
     if (n_out == 0) return UWSPR_B200_OK;
@@ -142,7 +143,9 @@ extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int s
                                            delay, fc / fs_in, d_out, (long long)out_stride, (long long)n_out);
     FE_CU(cudaGetLastError());
     if (space_out == UWSPR_B200_HOST)
-        FE_CU(cudaMemcpy(out, d_out_own, out_bytes, cudaMemcpyDeviceToHost));
+        // channel by channel: the caller's memory between two channels (out_stride > n_out) is not touched
+        FE_CU(cudaMemcpy2D(out, (size_t)out_stride * sizeof(float2), d_out_own, (size_t)out_stride * sizeof(float2),
+                           (size_t)n_out * sizeof(float2), (size_t)nchan, cudaMemcpyDeviceToHost));
     else
         FE_CU(cudaDeviceSynchronize());
     cudaFree(d_taps);

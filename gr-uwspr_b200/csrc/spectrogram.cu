@@ -289,7 +289,7 @@ k_worklist(const int *__restrict__ npk, int nwin, int cap, int *__restrict__ bas
     const int per = (nwin + 1023) / 1024;
     const int lo = min(nwin, tid * per), hi = min(nwin, lo + per);
     int s = 0;
-    for (int w = lo; w < hi; w++) s += npk[w];
+    for (int w = lo; w < hi; w++) s += max(npk[w], 0);
     part[tid] = s;
     __syncthreads();
     // Hillis-Steele inclusive scan over the 1024 partial sums
@@ -302,7 +302,7 @@ k_worklist(const int *__restrict__ npk, int nwin, int cap, int *__restrict__ bas
     int run = run0 + part[tid] - s;
     for (int w = lo; w < hi; w++) {
         base[w] = run;
-        const int n = npk[w];
+        const int n = max(npk[w], 0);   // the host rejects negative counts; never index below the list
         for (int q = 0; q < n; q++)
             if (run + q < cap) {
                 items[run + q].win = w;

@@ -173,9 +173,11 @@ receiver::receiver(const uwspr_b200_params_t &fdr_params, int shift_seconds, int
     d_cap = info.max_candidates;
     d_fl = p.fl;
     d_stride = shift_seconds * p.fs;
-    if (d_stride <= 0) {
+    // the reference's sliding window peeks fl - shift*fs samples after popping shift*fs (it needs shift*fs <= fl
+    // and does not check); a larger stride would also leave fewer than nwin*stride samples to retire after a flush
+    if (d_stride <= 0 || d_stride > d_fl) {
         uwspr_b200_destroy(d_ctx);
-        throw std::invalid_argument("receiver: shift*fs must be positive");
+        throw std::invalid_argument("receiver: need 0 < shift*fs <= fl");
     }
     d_npk.resize(d_batch);
     d_cands.resize(d_cap);

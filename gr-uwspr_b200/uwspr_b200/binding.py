@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
     "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack", "uwspr_b200_format_message_log",
     "uwspr_b200_pack_type1", "uwspr_b200_channel_symbols", "uwspr_b200_read_c2", "uwspr_b200_frontend",
-    "uwspr_b200_frontend_error",
+    "uwspr_b200_frontend_error", "uwspr_b200_coarse_fine_submit", "uwspr_b200_poll", "uwspr_b200_wait",
 ]
 
 CAND_DTYPE = np.dtype(
@@ -91,6 +91,12 @@ def load_library():
     L.uwspr_b200_fine.argtypes = [vp, vp, C.c_int, i64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.uwspr_b200_coarse_fine.restype = C.c_int
     L.uwspr_b200_coarse_fine.argtypes = [vp, vp, C.c_int, i64, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.uwspr_b200_coarse_fine_submit.restype = C.c_int
+    L.uwspr_b200_coarse_fine_submit.argtypes = L.uwspr_b200_coarse_fine.argtypes
+    L.uwspr_b200_poll.restype = C.c_int
+    L.uwspr_b200_poll.argtypes = [vp]
+    L.uwspr_b200_wait.restype = C.c_int
+    L.uwspr_b200_wait.argtypes = [vp]
     L.uwspr_b200_deinterleave.argtypes = [vp]
     L.uwspr_b200_fano.restype = C.c_int
     L.uwspr_b200_fano.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_uint32]
@@ -280,6 +286,28 @@ class Context:
                                                   _p(cands), cap, C.byref(total), _p(refined), _p(jig), _p(soft)))
         t = total.value
         return npk, cands[:t].copy(), refined[:t].copy(), jig[:t].copy(), soft[:t].copy()
+
+    def submit(self, samples, out, nwin=None, stride=None, jig_first=0, jig_count=NJIG):
+        """non-blocking coarse_fine into the caller's result buffers (result_buffers()); returns at once.
+        wait() returns the same tuple coarse_fine(out=...) returns; poll() says whether it is ready."""
+        stride = self.fl if stride is None else stride
+        ptr, space, keep = _samples_arg(samples)
+        nwin = self._nwin(samples, nwin, stride) if not isinstance(samples, tuple) else nwin
+        total = C.c_int32(0)
+        self._pending = (keep, out, nwin, total)
+        self._check(self.L.uwspr_b200_coarse_fine_submit(self.h, ptr, space, stride, nwin, jig_first, jig_count, _p(out["npk"]),
+                                                         _p(out["cands"]), self.info.max_candidates, C.byref(total),
+                                                         _p(out["refined"]), _p(out["jig"]), _p(out["soft"])))
+
+    def poll(self):
+        return int(self.L.uwspr_b200_poll(self.h))
+
+    def wait(self):
+        keep, out, nwin, total = self._pending
+        self._check(self.L.uwspr_b200_wait(self.h))
+        self._pending = None
+        t = total.value
+        return out["npk"][:nwin], out["cands"][:t], out["refined"][:t], out["jig"][:t], out["soft"][:t]
 
     def debug_spectrogram(self, win=0):
         ps = np.zeros((self.info.n_rows, self.info.n_bins), np.float32)

@@ -11,7 +11,8 @@
  * Radio types in any signature.  Every function returns an int status
  * (UWSPR_B200_OK == 0); nothing in the library calls exit() or throws across the
  * boundary (the reference exits on bad parameters, lib/FDR_impl.cc:85-90).
- * A context is bound to one CUDA device and may be used by one thread at a time;
+ * A context is bound to one CUDA device and may be used by one thread at a time
+ * (uwspr_b200_coarse_fine_submit / uwspr_b200_wait give a non-blocking form);
  * distinct contexts are independent (the reference's blocks are never re-entered
  * either: GNU Radio 3.7 runs one handler invocation at a time per block).
  *
@@ -106,7 +107,7 @@ UWSPR_B200_API int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b2
 UWSPR_B200_API void uwspr_b200_destroy(uwspr_b200_ctx *ctx);
 UWSPR_B200_API const char *uwspr_b200_last_error(const uwspr_b200_ctx *ctx);
 UWSPR_B200_API const char *uwspr_b200_status_string(int status);
-/* text of the failure of the last uwspr_b200_create that returned non-zero */
+/* text of the failure of the last uwspr_b200_create that returned non-zero on the calling thread */
 UWSPR_B200_API const char *uwspr_b200_create_error(void);
 
 /* Derived constants of the FDR constructor (FDR_impl.cc:81-137), for callers and tests. */
@@ -161,6 +162,22 @@ UWSPR_B200_API int uwspr_b200_coarse_fine(uwspr_b200_ctx *ctx, const float *samp
                                           uwspr_b200_candidate_t *cands, int cap, int32_t *total,
                                           uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig,
                                           uint8_t *soft);
+
+/* ---- non-blocking form of uwspr_b200_coarse_fine ----------------------------------------
+ * _submit starts the same work on a thread owned by the context and returns at once (a GNU Radio
+ * message handler does not stall for the batch); the caller keeps every buffer alive and untouched
+ * until uwspr_b200_wait() returns the call's status.  uwspr_b200_poll(): 1 = finished, 0 = still
+ * running, -1 = nothing submitted.  One submission per context at a time; the synchronous entry points
+ * return UWSPR_B200_E_STATE while one is outstanding.  Kernels run on the stream given to
+ * uwspr_b200_set_stream(), as for the synchronous calls. */
+UWSPR_B200_API int uwspr_b200_coarse_fine_submit(uwspr_b200_ctx *ctx, const float *samples, int space,
+                                                 int64_t win_stride, int nwin, int jig_first,
+                                                 int jig_count, int32_t *npk,
+                                                 uwspr_b200_candidate_t *cands, int cap, int32_t *total,
+                                                 uwspr_b200_refined_t *refined,
+                                                 uwspr_b200_jiggle_t *jig, uint8_t *soft);
+UWSPR_B200_API int uwspr_b200_poll(uwspr_b200_ctx *ctx);
+UWSPR_B200_API int uwspr_b200_wait(uwspr_b200_ctx *ctx);
 
 /* ---- host side of the path that stays on the CPU (north_star: "Fano decoding and
  * WSPR_unpacker stay host-side") -------------------------------------------------------- */

@@ -36,29 +36,7 @@ def ctx_for(maxdrift=0, halfbandwidth=10, threshold=10, max_windows=64, **kw):
     return _ctx_cache[key]
 
 
-def cands_equal_exact(a, b):
-    """every field identical; snr alone is compared to 4 ulp: it is 10*log10f(x), and libm's
-    log10f is not correctly rounded (the value depends on the glibc version of the host the
-    reference runs on), while the CUDA path rounds a double-precision log10"""
-    if len(a) != len(b):
-        return False
-    ca, cb = td.canon_cands(a), td.canon_cands(b)
-    if not np.allclose(ca["snr"], cb["snr"], rtol=5e-7, atol=1e-6):
-        return False
-    ca["snr"] = 0
-    cb["snr"] = 0
-    return ca.tobytes() == cb.tobytes()
-
-
-def oracle_on_gpu_ps(of, ctx, x, win=0):
-    """oracle normalizer + coarse search fed with the GPU's power spectrogram"""
-    ps = of.spectrogram(x)
-    gps, gpsavg = ctx.debug_spectrogram(win)
-    lo, nb = ctx.info.bin_lo, ctx.info.n_bins
-    ps_o = ps[:, lo:lo + nb].copy()
-    ps[:, lo:lo + nb] = gps
-    c0, psavg, _ = of.normalize_peaks(ps)
-    return of.coarse(ps, c0), ps_o, gps, psavg[lo:lo + nb], gpsavg
+from oracle.verify import cands_equal_exact, oracle_on_gpu_ps  # noqa: E402
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -524,3 +502,74 @@ def test_host_fed_tail_pieces(piece, groups, stride, monkeypatch):
     for u, v in zip(want[2:], fine):
         assert u.tobytes() == v.tobytes()
     small.close()
+
+
+def test_async_submit_equals_the_blocking_call():
+    """uwspr_b200_coarse_fine_submit / _poll / _wait: same bytes as the blocking call, the blocking entry points refuse
+    to run while a submission is outstanding"""
+    xs, _ = td.synth_batch(24, stream=52)
+    ctx = ub.Context(maxdrift=4, max_windows=24)
+    want = ctx.coarse_fine(xs)
+    out = ctx.result_buffers(24)
+    assert ctx.poll() == -1
+    ctx.submit(xs, out)
+    with pytest.raises(ub.UwsprError) as e:
+        ctx.coarse(xs)
+    assert e.value.status == 5
+    got = ctx.wait()
+    assert ctx.poll() == -1
+    for u, v in zip(want, got):
+        assert u.tobytes() == np.asarray(v).tobytes()
+    ctx.close()
+
+
+def test_fine_rejects_inconsistent_candidate_lists():
+    """the caller's npk / total are checked on the host before anything is uploaded"""
+    x, _ = td.synth_window(0, 1, snr_db=-10.0)
+    ctx = ctx_for(maxdrift=0, max_windows=64)
+    npk, cands = ctx.coarse(np.stack([x, x]))
+    assert npk.sum() == len(cands) >= 2
+    for bad in (np.array([-1, len(cands) + 1], np.int32), np.array([len(cands), 1], np.int32)):
+        with pytest.raises(ub.UwsprError) as e:
+            ctx.fine(np.stack([x, x]), bad, cands)
+        assert e.value.status == 1
+    # and a failed call does not leave a candidate list behind for fine(cands=None)
+    with pytest.raises(ub.UwsprError) as e:
+        ctx.fine(np.stack([x, x]))
+    assert e.value.status == 5
+    r = ctx.fine(np.stack([x, x]), npk, cands)       # the context is still usable
+    assert r[0]["worth_a_try"].any()
+
+
+def test_parity_config3_slice_against_the_reference_chain():
+    """1 024 windows of the bench generator (BASELINE.json configs[2] statistics, maxdrift 4) through coarse_fine and,
+    on the SAME samples, through the reference chain on the host (oracle/verify.py: the unmodified reference where
+    oracle/_ref is built): no refined / soft-symbol / message difference; candidate-set differences, if any, are all
+    reproduced by the oracle's post-FFT chain on the GPU's own spectrogram (FFT rounding)"""
+    import torch
+    from oracle import verify as vf
+    from uwspr_b200 import synth
+    nwin = 1024
+    params = dict(fs=375, fl=45000, spb=256, maxdrift=4, maxfreqs=200, halfbandwidth=10, cf=1500, threshold=10)
+    xs_t, truth = synth.gen_frames(0, nwin, 0, torch.device("cuda", 0))
+    xs = xs_t.cpu().numpy()
+    ctx = ub.Context(max_windows=nwin, **params)
+    npk, cands, refined, jig, soft = ctx.coarse_fine(xs)
+    dec = ub.decode_candidates(refined, jig, soft)
+    win = np.repeat(np.arange(nwin), npk)
+    msgs = [[] for _ in range(nwin)]
+    for g, m, _ in dec:
+        msgs[int(win[g])].append(bytes(m))
+
+    def dbg(n):
+        c = ub.Context(max_windows=n, **params)
+        c.set_debug(True)
+        return c
+    r = vf.verify(xs.reshape(-1), 45000, nwin, params, npk, cands, refined, jig, soft, msgs, full_jiggle_windows=128, make_debug_context=dbg)
+    print(r)
+    assert r["windows"] == nwin
+    assert r["refined_mismatch"] == 0 and r["soft_symbol_mismatch"] == 0
+    assert r["cand_set_mismatch"] == r.get("explained_by_fft_rounding", 0)
+    assert r["message_mismatch"] <= r["cand_set_mismatch"]
+    assert sum(bytes(truth[w]["msg"]) in msgs[w] for w in range(nwin)) >= 0.9 * nwin
+    ctx.close()
