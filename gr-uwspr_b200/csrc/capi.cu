@@ -46,9 +46,8 @@ struct Knobs {
     bool no_early_d2h = false;  // UWSPR_B200_NO_EARLY_D2H
     bool trace = false;         // UWSPR_B200_TRACE
     int dev_chunks = 1;         // UWSPR_B200_DEV_CHUNKS
-    int stagger_fine_us = 0;    // UWSPR_B200_STAGGER_FINE_US / _COARSE_US: start offset between the CTAs that share an SM
-    int stagger_coarse_us = 0;
     int fine_ctas_per_sm = 0;   // UWSPR_B200_FINE_CTAS_PER_SM: fewer resident CTAs than fit (occupancy experiments)
+    int fine_slice = 16384;     // UWSPR_B200_FINE_SLICE: candidates per pass of the fine path's stage sequence
 };
 
 Knobs read_knobs()
@@ -65,9 +64,8 @@ Knobs read_knobs()
     k.no_early_d2h = getenv("UWSPR_B200_NO_EARLY_D2H") != nullptr;
     k.trace = getenv("UWSPR_B200_TRACE") != nullptr;
     k.dev_chunks = std::max(1, geti("UWSPR_B200_DEV_CHUNKS", 1));
-    k.stagger_fine_us = std::max(0, geti("UWSPR_B200_STAGGER_FINE_US", 0));
-    k.stagger_coarse_us = std::max(0, geti("UWSPR_B200_STAGGER_COARSE_US", 0));
     k.fine_ctas_per_sm = std::max(0, geti("UWSPR_B200_FINE_CTAS_PER_SM", 0));
+    k.fine_slice = std::max(1, geti("UWSPR_B200_FINE_SLICE", k.fine_slice));
     return k;
 }
 
@@ -88,7 +86,11 @@ struct Buffers {
     uwspr_b200_refined_t *refined = nullptr;
     uwspr_b200_jiggle_t *jig = nullptr;
     uint8_t *soft = nullptr;
-    int *sm_slots = nullptr;  // 2 x 256 arrival counters per SM (uw_stagger)
+    int *fine_tickets = nullptr;  // work counters of the fine path's heavy launches, 16 per compute stream
+    // fine path workspaces, one per compute stream (chunks on different streams run concurrently)
+    void *fine_state[3] = { nullptr, nullptr, nullptr };
+    void *fine_pbuf[3] = { nullptr, nullptr, nullptr };
+    void *fine_pe[3] = { nullptr, nullptr, nullptr };
     int *counters = nullptr;  // [0] running total, [1] overflow; set s at 4+4s: ticket coarse, ticket fine, end of chunk
     // tables
     float *window = nullptr;
@@ -105,7 +107,8 @@ struct uwspr_b200_ctx {
     Buffers b;
     int device = 0, sm_count = 0;
     int chunk_windows = 0, max_windows = 0, max_candidates = 0;
-    int grid_coarse = 0, grid_fine = 0;
+    int grid_coarse = 0, grid_points = 0, grid_lags = 0;
+    int fine_slice[3] = { 0, 0, 0 };   // candidates the fine path's stage sequence handles per pass, per compute stream
     cudaStream_t compute = nullptr, compute2 = nullptr, compute3 = nullptr, copy = nullptr, d2h = nullptr;
     int *h_ends = nullptr;  // pinned: end of every chunk's items (host-fed calls stream results back per chunk)
     bool own_compute = true;
@@ -446,14 +449,20 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
         if (early) CU(cudaMemcpyAsync(&ctx->h_ends[c], set + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (do_coarse) {
             uw_launch_coarse(d, amp, peaks, b.items, set + 2, ctx->max_candidates, b.off4, b.hyp_unique, b.cands, set,
-                             ctx->grid_coarse, kn.stagger_coarse_us, ctx->grid_coarse / ctx->sm_count, b.sm_slots, st);
+                             ctx->grid_coarse, st);
             ctx->launches++;
         }
         CU(cudaEventRecord(e[2], st));
         if (do_fine) {
-            uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 2, ctx->max_candidates, b.cands, jig_first,
-                           jig_count, b.refined, b.jig, b.soft, set + 1, ctx->grid_fine, kn.stagger_fine_us, ctx->grid_fine / ctx->sm_count, b.sm_slots + 256, st);
-            ctx->launches++;
+            // the stage sequence runs over slices of at most fine_slice candidates (the workspace size); the
+            // number of candidates is a device value, so the launches cover the most the chunk can hold
+            const long long most = std::min<long long>(ctx->max_candidates, (long long)nw * d.maxcand);
+            const int slice = ctx->fine_slice[ch.strm];
+            for (long long s0 = 0; s0 < most; s0 += slice)
+                ctx->launches += uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 1, set + 2, ctx->max_candidates, b.cands,
+                                                jig_first, jig_count, b.refined, b.jig, b.soft, (int)s0, slice,
+                                                b.fine_state[ch.strm], b.fine_pbuf[ch.strm], b.fine_pe[ch.strm], b.fine_tickets + 16 * ch.strm, ctx->grid_points,
+                                                ctx->grid_lags, st);
         }
         CU(cudaEventRecord(e[3], st));
         if (host) CU(cudaEventRecord(ctx->ev_free[s], st));
@@ -652,8 +661,16 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaMalloc(&b.soft, cap * UWSPR_B200_NJIG * UW_NSYM));
     CUC(cudaMalloc(&b.counters, kCounterInts * sizeof(int)));
     CUC(cudaMemset(b.counters, 0, kCounterInts * sizeof(int)));
-    CUC(cudaMalloc(&b.sm_slots, 512 * sizeof(int)));
-    CUC(cudaMemset(b.sm_slots, 0, 512 * sizeof(int)));
+    CUC(cudaMalloc(&b.fine_tickets, 48 * sizeof(int)));
+    CUC(cudaMemset(b.fine_tickets, 0, 48 * sizeof(int)));
+    // the first stream carries the large chunks of device-resident input; the other two only see host-fed chunks
+    // (<= 1024 windows, pieces of a quarter of that)
+    for (int q = 0; q < 3; q++) {
+        ctx->fine_slice[q] = std::max(1, std::min(ctx->max_candidates, q == 0 ? ctx->knobs.fine_slice : std::min(ctx->knobs.fine_slice, 4096)));
+        CUC(cudaMalloc(&b.fine_state[q], (size_t)ctx->fine_slice[q] * uw_fine_state_bytes()));
+        CUC(cudaMalloc(&b.fine_pbuf[q], (size_t)ctx->fine_slice[q] * uw_fine_pbuf_bytes()));
+        CUC(cudaMalloc(&b.fine_pe[q], (size_t)ctx->fine_slice[q] * uw_fine_pe_bytes()));
+    }
     // tables
     std::vector<float> window(UW_FFT_N);
     for (int i = 0; i < d.size; i++) window[i] = (float)sin((M_PI / (d.size - 1)) * i);  // FDR_impl.cc:103-105
@@ -693,8 +710,19 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     if (uw_coarse_setup(d) || uw_fine_setup())
         return bail(fail(ctx, UWSPR_B200_E_CUDA, "cannot reserve shared memory for the kernels (not an sm_100a device?)"));
     ctx->grid_coarse = ctx->sm_count * uw_coarse_blocks_per_sm(d);
-    ctx->grid_fine = ctx->sm_count * uw_fine_blocks_per_sm();
-    if (ctx->knobs.fine_ctas_per_sm > 0) ctx->grid_fine = ctx->sm_count * std::min(ctx->knobs.fine_ctas_per_sm, uw_fine_blocks_per_sm());
+    {
+        int bp = 1, bl = 1;
+        uw_fine_blocks_per_sm(&bp, &bl);
+        if (ctx->knobs.fine_ctas_per_sm > 0) {
+            bp = std::min(bp, ctx->knobs.fine_ctas_per_sm);
+            bl = std::min(bl, ctx->knobs.fine_ctas_per_sm);
+        }
+        ctx->grid_points = ctx->sm_count * bp;
+        ctx->grid_lags = ctx->sm_count * bl;
+        if (ctx->knobs.trace)
+            fprintf(stderr, "uwspr_b200 trace: fine path: %d + %d resident CTAs per SM (points, lags), slices of %d candidates\n", bp, bl,
+                    std::max(1, std::min(ctx->max_candidates, ctx->knobs.fine_slice)));
+    }
     CUC(cudaDeviceSynchronize());
 #undef CUC
     *ctx_out = ctx;
@@ -708,7 +736,8 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
     void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
-                     b.cands, b.refined, b.jig, b.soft, b.counters, b.sm_slots, b.window, b.twiddle, b.off4, b.hyp_unique };
+                     b.cands, b.refined, b.jig, b.soft, b.counters, b.fine_tickets, b.fine_state[0], b.fine_state[1], b.fine_state[2], b.fine_pbuf[0], b.fine_pbuf[1],
+                     b.fine_pbuf[2], b.fine_pe[0], b.fine_pe[1], b.fine_pe[2], b.window, b.twiddle, b.off4, b.hyp_unique };
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kThreads)
 k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ peaks,
          const UwItem *__restrict__ items, const int *__restrict__ total_ptr, int cap,
          const uint32_t *__restrict__ off4_g, const short *__restrict__ hyp_unique_g,
-         uwspr_b200_candidate_t *__restrict__ cands, int *__restrict__ ticket, int stagger_us, int ctas_per_sm, int *__restrict__ slots)
+         uwspr_b200_candidate_t *__restrict__ cands, int *__restrict__ ticket)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const CoarseLayout L = coarse_layout(d.n_rows, d.tile_w, d.n_unique, d.n_hyp);
@@ -75,7 +75,6 @@ k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ pea
     const int U = d.n_unique, S = L.tile_stride;
     const int total = min(*total_ptr, cap);
 
-    uw_stagger(stagger_us, ctas_per_sm, slots);
     for (int t = tid; t < UW_NQUAD * U; t += kThreads) off4[t] = off4_g[t];
     for (int t = tid; t < d.n_hyp; t += kThreads) hmap[t] = hyp_unique_g[t];
     if (tid == 0) {
@@ -107,40 +106,50 @@ k_coarse(UwDims d, const float *__restrict__ amp, const UwPeak *__restrict__ pea
         // one or two tile rows, so shared loads are broadcasts / conflict free)
         for (int task = tid; task < UW_NK0 * U; task += kThreads) {
             const int k0 = task / U, u = task - k0 * U;
-            float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f, ss4 = 0.f;
-            float pw0 = 0.f, pw1 = 0.f, pw2 = 0.f, pw3 = 0.f, pw4 = 0.f;
+            // bins 0,1 and 2,3 are carried as packed pairs (FADD2 / FFMA2, common.cuh), bin 4 as scalars: every
+            // lane of every instruction performs one of the reference's additions with its own rounding.
+            // The sign of the sync bit enters as fma(+-1, d, ss): the product is exact, so the result is the
+            // correctly rounded ss +- d, i.e. exactly fadd(ss, +-d).
+            // Each symbol reads one copy of the accumulator pairs and writes the other (x -> y -> x ...): ptxas
+            // otherwise moves every packed accumulator back to its loop-entry register pair after each symbol.
+            uw_f2 ss01 = uw_pk(0.f, 0.f), ss23 = uw_pk(0.f, 0.f), pw01 = uw_pk(0.f, 0.f), pw23 = uw_pk(0.f, 0.f);
+            uw_f2 ss01y, ss23y, pw01y, pw23y;
+            float ss4 = 0.f, pw4 = 0.f;
             const float *rowp = tile + k0 * S;
+#define UW_COARSE_SYMBOL(E, SS01I, SS23I, PW01I, PW23I, SS01O, SS23O, PW01O, PW23O)                                 \
+    do {                                                                                                            \
+        const float *A = rowp + ((w >> (8 * (E))) & 0xffu);                                                         \
+        const uw_f2 a01 = uw_pk(A[0], A[1]), a23 = uw_pk(A[2], A[3]), a45 = uw_pk(A[4], A[5]);                      \
+        const uw_f2 a67 = uw_pk(A[6], A[7]), a89 = uw_pk(A[8], A[9]);                                               \
+        const float a10 = A[10];                                                                                    \
+        /* pair sums A[x] + A[x+4]: (p0+p2) of bin x and (p1+p3) of bin x-2 */                                      \
+        const uw_f2 s01 = uw_add2(a01, a45), s23 = uw_add2(a23, a67), s45 = uw_add2(a45, a89);                      \
+        const float s6 = __fadd_rn(uw_lo(a67), a10);                                                                \
+        /* powersum(): ss += (2*pr3[k]-1) * ((p1+p3)-(p0+p2)) */                                                    \
+        const float sgn = ((sbits >> (E)) & 1u) ? 1.0f : -1.0f;                                                     \
+        SS01O = uw_fma2(uw_pk(sgn, sgn), uw_sub2(s23, s01), SS01I);                                                 \
+        SS23O = uw_fma2(uw_pk(sgn, sgn), uw_sub2(s45, s23), SS23I);                                                 \
+        ss4 = fmaf(sgn, __fsub_rn(s6, uw_lo(s45)), ss4);                                                            \
+        /* pow = pow + p0 + p1 + p2 + p3, left to right */                                                          \
+        PW01O = uw_add2(uw_add2(uw_add2(uw_add2(PW01I, a01), a23), a45), a67);                                      \
+        PW23O = uw_add2(uw_add2(uw_add2(uw_add2(PW23I, a23), a45), a67), a89);                                      \
+        pw4 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pw4, uw_lo(a45)), uw_lo(a67)), uw_lo(a89)), a10);             \
+        rowp += 2 * S;                                                                                              \
+    } while (0)
             for (int q = 0; q < UW_NQUAD; q++) {
-                uint32_t w = off4[q * U + u];
+                const uint32_t w = off4[q * U + u];
                 const uint32_t sbits = s_sync[(4 * q) >> 5] >> ((4 * q) & 31);  // 4 | 32: no straddle
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (4 * q + e < UW_NSYM) {
-                        const float *A = rowp + (w & 0xffu);
-                        w >>= 8;
-                        const float a0 = A[0], a1 = A[1], a2 = A[2], a3 = A[3], a4 = A[4], a5 = A[5];
-                        const float a6 = A[6], a7 = A[7], a8 = A[8], a9 = A[9], a10 = A[10];
-                        // pair sums A[x] + A[x+4]: (p0+p2) of bin x and (p1+p3) of bin x-2
-                        const float s0 = __fadd_rn(a0, a4), s1 = __fadd_rn(a1, a5), s2 = __fadd_rn(a2, a6);
-                        const float s3 = __fadd_rn(a3, a7), s4 = __fadd_rn(a4, a8), s5 = __fadd_rn(a5, a9);
-                        const float s6 = __fadd_rn(a6, a10);
-                        // powersum(): ss += (2*pr3[k]-1) * ((p1+p3)-(p0+p2));  -(x-y) == (y-x) exactly
-                        const uint32_t neg = ((sbits >> e) & 1u) ? 0u : 0x80000000u;
-                        ss0 = __fadd_rn(ss0, __uint_as_float(__float_as_uint(__fsub_rn(s2, s0)) ^ neg));
-                        ss1 = __fadd_rn(ss1, __uint_as_float(__float_as_uint(__fsub_rn(s3, s1)) ^ neg));
-                        ss2 = __fadd_rn(ss2, __uint_as_float(__float_as_uint(__fsub_rn(s4, s2)) ^ neg));
-                        ss3 = __fadd_rn(ss3, __uint_as_float(__float_as_uint(__fsub_rn(s5, s3)) ^ neg));
-                        ss4 = __fadd_rn(ss4, __uint_as_float(__float_as_uint(__fsub_rn(s6, s4)) ^ neg));
-                        // pow = pow + p0 + p1 + p2 + p3, left to right
-                        pw0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pw0, a0), a2), a4), a6);
-                        pw1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pw1, a1), a3), a5), a7);
-                        pw2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pw2, a2), a4), a6), a8);
-                        pw3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pw3, a3), a5), a7), a9);
-                        pw4 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pw4, a4), a6), a8), a10);
-                        rowp += 2 * S;
-                    }
+                UW_COARSE_SYMBOL(0, ss01, ss23, pw01, pw23, ss01y, ss23y, pw01y, pw23y);
+                UW_COARSE_SYMBOL(1, ss01y, ss23y, pw01y, pw23y, ss01, ss23, pw01, pw23);
+                static_assert(UW_NSYM % 4 == 2, "the last quad holds two symbols");
+                if (4 * q + 2 < UW_NSYM) {
+                    UW_COARSE_SYMBOL(2, ss01, ss23, pw01, pw23, ss01y, ss23y, pw01y, pw23y);
+                    UW_COARSE_SYMBOL(3, ss01y, ss23y, pw01y, pw23y, ss01, ss23, pw01, pw23);
                 }
             }
+#undef UW_COARSE_SYMBOL
+            const float ss0 = uw_lo(ss01), ss1 = uw_hi(ss01), ss2 = uw_lo(ss23), ss3 = uw_hi(ss23);
+            const float pw0 = uw_lo(pw01), pw1 = uw_hi(pw01), pw2 = uw_lo(pw23), pw3 = uw_hi(pw23);
             float *sv = syncv + k0 * U + u;
             sv[0 * UW_NK0 * U] = __fdiv_rn(ss0, pw0);
             sv[1 * UW_NK0 * U] = __fdiv_rn(ss1, pw1);
@@ -260,10 +269,10 @@ int uw_coarse_setup(const UwDims &d)
 
 void uw_launch_coarse(const UwDims &d, const float *amp, const UwPeak *peaks, const UwItem *items,
                       const int *total, int cap, const uint32_t *off4, const short *hyp_unique,
-                      uwspr_b200_candidate_t *cands, int *ticket, int grid, int stagger_us, int ctas_per_sm, int *slots, cudaStream_t s)
+                      uwspr_b200_candidate_t *cands, int *ticket, int grid, cudaStream_t s)
 {
     k_coarse<<<grid, kThreads, uw_coarse_smem_bytes(d), s>>>(d, amp, peaks, items, total, cap, off4,
-                                                             hyp_unique, cands, ticket, stagger_us, ctas_per_sm, slots);
+                                                             hyp_unique, cands, ticket);
 }
 
 int uw_coarse_blocks_per_sm(const UwDims &d)

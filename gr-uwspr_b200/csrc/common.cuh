@@ -50,31 +50,6 @@ __device__ __forceinline__ int uw_sync_bit(const uint32_t *words, int i)
     return (int)((words[i >> 5] >> (i & 31)) & 1u);
 }
 
-// Start offset between the CTAs that share an SM.  Every candidate costs nearly the same, so
-// co-resident CTAs of a persistent grid that start together stay in the same phase of their stage
-// sequence for the whole launch and their sparse phases (stage tails, single-warp replays) coincide; a
-// one-off offset of a fraction of a candidate's duration keeps them apart.  `slots` holds one counter
-// per SM (never reset: arrival order modulo the CTAs per SM is all that matters).
-__device__ __forceinline__ void uw_stagger(int us_per_class, int ctas_per_sm, int *slots)
-{
-    if (us_per_class <= 0) return;
-    if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        const int cls = atomicAdd(&slots[smid & 255], 1) % ctas_per_sm;
-        if (cls > 0) {
-            unsigned long long t0, t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            const unsigned long long wait_ns = (unsigned long long)cls * (unsigned long long)us_per_class * 1000ull;
-            do {
-                __nanosleep(2000);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            } while (t - t0 < wait_ns);
-        }
-    }
-    __syncthreads();
-}
-
 // ---- packed fp32 pairs (sm_100a: add/sub/fma.rn.f32x2 -> FADD2 / FFMA2) ------------------
 // One issue slot carries two independent IEEE round-to-nearest operations, each bit-identical
 // to its scalar form.  The kernels that mirror reference sums are bound by issue slots and
@@ -125,6 +100,13 @@ __device__ __forceinline__ uw_f2 uw_mul2(uw_f2 a, uw_f2 b, uw_f2 nz)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
     return r;
 }
+// a*b + c with one rounding per lane (callers use it where the product is exact)
+__device__ __forceinline__ uw_f2 uw_fma2(uw_f2 a, uw_f2 b, uw_f2 c)
+{
+    uw_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 // scalar times pair (the scalar is broadcast by the instruction's operand form)
 __device__ __forceinline__ uw_f2 uw_mul2s(float a, uw_f2 b, uw_f2 nz) { return uw_mul2(uw_pk(a, a), b, nz); }
 
@@ -136,14 +118,17 @@ void uw_launch_worklist(const int *npk, int nwin, int cap, int *base, UwItem *it
                         int *set, cudaStream_t s);
 void uw_launch_coarse(const UwDims &d, const float *amp, const UwPeak *peaks, const UwItem *items,
                       const int *total, int cap, const uint32_t *off4, const short *hyp_unique,
-                      uwspr_b200_candidate_t *cands, int *ticket, int grid, int stagger_us, int ctas_per_sm, int *slots, cudaStream_t s);
-void uw_launch_fine(const UwDims &d, const float2 *x, long long win_stride, const UwItem *items,
-                    const int *total, int cap, const uwspr_b200_candidate_t *cands, int jig_first,
-                    int jig_count, uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig,
-                    uint8_t *soft, int *ticket, int grid, int stagger_us, int ctas_per_sm, int *slots, cudaStream_t s);
+                      uwspr_b200_candidate_t *cands, int *ticket, int grid, cudaStream_t s);
+// the stage sequence of the fine path over work-list entries *begin + slice0 + [0, slice_n); returns the launches issued
+int uw_launch_fine(const UwDims &d, const float2 *x, long long win_stride, const UwItem *items, const int *begin,
+                   const int *end, int cap, const uwspr_b200_candidate_t *cands, int jig_first, int jig_count,
+                   uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft, int slice0, int slice_n,
+                   void *state, void *pbuf, void *pE, int *tickets, int grid_points, int grid_lags, cudaStream_t s);
+size_t uw_fine_state_bytes();   // per candidate of a slice: chain state, stage magnitudes, jiggle magnitudes
+size_t uw_fine_pbuf_bytes();
+size_t uw_fine_pe_bytes();
+void uw_fine_blocks_per_sm(int *points, int *lags);
 size_t uw_coarse_smem_bytes(const UwDims &d);
-size_t uw_fine_smem_bytes();
 int uw_coarse_setup(const UwDims &d);
 int uw_fine_setup();
 int uw_coarse_blocks_per_sm(const UwDims &d);
-int uw_fine_blocks_per_sm();
