@@ -480,14 +480,16 @@ def run_ours(args):
     alg_flops = tot_windows * FLOP_SPEC + tot_cand * flop_coarse(PARAMS["maxdrift"]) + tot_evals * FLOP_POINT
     info_nbp = 44
     fine_alg_t = evals * FLOP_POINT / (fine_ms * 1e-3) / 1e12
-    # executed fp32 lane-operations of the fine kernel per candidate: the chain evaluates 19 new points with
-    # routine R1 (14 per tone-sample) and 17 jiggles with R2 (8 per lag + 6 per lag group of <= 5, 4 groups)
+    # executed fp32 lane-operations of the fine path per candidate: the chain evaluates 19 new points with
+    # routine R1 (14 mul/add per tone-sample: 8 for the two correlations, 6 for the table rotation) and 17 jiggles
+    # with R2 (8 per lag + 6 per lag group of <= 5, 4 groups); the packed forms carry two of them per instruction
     fine_exec = gated * (19 * 14 + (17 * 8 + 4 * 6)) * 162 * 4 * 256 + (ncand - gated) * 11 * 14 * 162 * 4 * 256
     fine_exec_t = fine_exec / (fine_ms * 1e-3) / 1e12
     coarse_alg_t = ncand * flop_coarse(PARAMS["maxdrift"]) / (coarse_ms * 1e-3) / 1e12
     spec_bytes = nwin * (360000.0 + 348 * info_nbp * 4)
     rooflines = [
-        dict(kernel="k_fine", ms=fine_ms, bound="fp32 pipe, non-fused (separately rounded mul and add, as the reference's sums require)",
+        dict(kernel="fine path: k_fine_points (stages A-D) + k_fine_lags (stage E) + k_fine_step / k_fine_finish", ms=fine_ms,
+             bound="fp32 pipe, non-fused (separately rounded mul and add, as the reference's sums require)",
              algorithmic=dict(achieved=fine_alg_t, unit="TFLOP/s", frac_of_fma_peak=fine_alg_t / FP32_FMA_PEAK, frac_of_nonfused_peak=fine_alg_t / FP32_NONFUSED_PEAK,
                               note="reference operation count: 162 x 4 x 256 x 8 flop per evaluated point (SURVEY 8(d))"),
              executed=dict(achieved=fine_exec_t, unit="T lane-op/s", frac_of_nonfused_peak=fine_exec_t / FP32_NONFUSED_PEAK,
@@ -517,8 +519,9 @@ def run_ours(args):
                         "(uwspr_b200.sharding.balanced_counts); same total as the equal split" if balance else "equal")),
         gpu_launches=int(launches),
         stage_ms=dict(spectrogram_normalizer=spec_ms, coarse_search=coarse_ms, fine_sync_demod=fine_ms, call=float(st[3])),
-        roofline=dict(bound="hbm", kernel="k_fine (fine sync + soft symbols)", achieved=alg_bytes / (fine_ms * 1e-3) / 1e9, peak=hbm_peak,
+        roofline=dict(bound="hbm", kernel="fine path (k_fine_points + k_fine_lags: fine sync + soft symbols)", achieved=alg_bytes / (fine_ms * 1e-3) / 1e9, peak=hbm_peak,
                       unit="GB/s", frac=alg_bytes / (fine_ms * 1e-3) / 1e9 / hbm_peak, traffic=recorded_traffic(nwin),
+                      launches_per_step="the fine path is a sequence of launches per slice of candidates; `achieved` uses their summed device time",
                       peak_source="MEASURED_PEAKS.json (measured copy)" if peaks else "fallback 6650 GB/s",
                       note="the dominant kernel is FP32-pipe bound, not HBM bound: see rooflines[0]"),
         rooflines=rooflines,

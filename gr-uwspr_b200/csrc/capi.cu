@@ -39,7 +39,7 @@ struct UwChunk {
 // Tuning / diagnosis knobs, read from the environment once, when the context is created
 // (DESIGN.md section 3 lists them).
 struct Knobs {
-    int host_chunk = 1024;      // UWSPR_B200_HOST_CHUNK: windows per host-fed chunk
+    int host_chunk = 0;         // UWSPR_B200_HOST_CHUNK: windows per host-fed chunk (0: nwin/16 within [1024, 4096])
     int tail_groups = 2;        // UWSPR_B200_TAIL_GROUPS: chunk groups at the end of a host-fed call that are cut up
     int tail_piece = 0;         // UWSPR_B200_TAIL_PIECE: windows per piece (0: a quarter chunk)
     bool no_tail_split = false; // UWSPR_B200_NO_TAIL_SPLIT
@@ -57,7 +57,7 @@ Knobs read_knobs()
         const char *e = getenv(name);
         return e ? atoi(e) : def;
     };
-    k.host_chunk = std::max(1, geti("UWSPR_B200_HOST_CHUNK", k.host_chunk));
+    k.host_chunk = std::max(0, geti("UWSPR_B200_HOST_CHUNK", k.host_chunk));
     k.tail_groups = std::max(0, std::min(2, geti("UWSPR_B200_TAIL_GROUPS", k.tail_groups)));
     k.tail_piece = std::max(0, geti("UWSPR_B200_TAIL_PIECE", 0));
     k.no_tail_split = getenv("UWSPR_B200_NO_TAIL_SPLIT") != nullptr;
@@ -91,6 +91,7 @@ struct Buffers {
     void *fine_state[3] = { nullptr, nullptr, nullptr };
     void *fine_pbuf[3] = { nullptr, nullptr, nullptr };
     void *fine_pe[3] = { nullptr, nullptr, nullptr };
+    void *fine_tables[3] = { nullptr, nullptr, nullptr };
     int *counters = nullptr;  // [0] running total, [1] overflow; set s at 4+4s: ticket coarse, ticket fine, end of chunk
     // tables
     float *window = nullptr;
@@ -320,7 +321,11 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
     // previous chunk's fine kernel
     const Knobs &kn = ctx->knobs;
     const bool two = host || kn.dev_chunks > 1;
-    const int cw = host ? std::max(1, std::min(kn.host_chunk, ctx->chunk_windows / 2))
+    // host-fed chunk: small enough that the first kernels start early and little is left after the last byte, large
+    // enough that the fine path's launches are well filled (measured on a 100 000-window overlapped stream: 1024 /
+    // 2048 / 4096 windows per chunk -> 235 / 248 / 251 k windows/s; a 10 000-window call does not care)
+    const int host_chunk = kn.host_chunk > 0 ? kn.host_chunk : std::min(4096, std::max(1024, nwin / 16));
+    const int cw = host ? std::max(1, std::min(host_chunk, ctx->chunk_windows / 2))
                         : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + kn.dev_chunks - 1) / kn.dev_chunks))
                                : ctx->chunk_windows);
     // Chunk schedule.  With host input the kernels of a chunk cannot start before its last byte
@@ -461,7 +466,7 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
             for (long long s0 = 0; s0 < most; s0 += slice)
                 ctx->launches += uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 1, set + 2, ctx->max_candidates, b.cands,
                                                 jig_first, jig_count, b.refined, b.jig, b.soft, (int)s0, slice,
-                                                b.fine_state[ch.strm], b.fine_pbuf[ch.strm], b.fine_pe[ch.strm], b.fine_tickets + 16 * ch.strm, ctx->grid_points,
+                                                b.fine_state[ch.strm], b.fine_pbuf[ch.strm], b.fine_pe[ch.strm], b.fine_tables[ch.strm], b.fine_tickets + 16 * ch.strm, ctx->grid_points,
                                                 ctx->grid_lags, st);
         }
         CU(cudaEventRecord(e[3], st));
@@ -670,6 +675,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
         CUC(cudaMalloc(&b.fine_state[q], (size_t)ctx->fine_slice[q] * uw_fine_state_bytes()));
         CUC(cudaMalloc(&b.fine_pbuf[q], (size_t)ctx->fine_slice[q] * uw_fine_pbuf_bytes()));
         CUC(cudaMalloc(&b.fine_pe[q], (size_t)ctx->fine_slice[q] * uw_fine_pe_bytes()));
+        CUC(cudaMalloc(&b.fine_tables[q], (size_t)ctx->fine_slice[q] * uw_fine_tables_bytes()));
     }
     // tables
     std::vector<float> window(UW_FFT_N);
@@ -737,7 +743,7 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     Buffers &b = ctx->b;
     void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
                      b.cands, b.refined, b.jig, b.soft, b.counters, b.fine_tickets, b.fine_state[0], b.fine_state[1], b.fine_state[2], b.fine_pbuf[0], b.fine_pbuf[1],
-                     b.fine_pbuf[2], b.fine_pe[0], b.fine_pe[1], b.fine_pe[2], b.window, b.twiddle, b.off4, b.hyp_unique };
+                     b.fine_pbuf[2], b.fine_pe[0], b.fine_pe[1], b.fine_pe[2], b.fine_tables[0], b.fine_tables[1], b.fine_tables[2], b.window, b.twiddle, b.off4, b.hyp_unique };
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);

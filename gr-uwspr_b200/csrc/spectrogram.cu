@@ -11,7 +11,11 @@
 // One CTA (256 threads) per window.  Four 64-thread groups each run one radix-8x8x8
 // Stockham FFT per iteration (87 iterations cover the 348 rows); the two inter-pass
 // exchanges go through shared memory, the window and twiddles live in registers / shared
-// memory.  Only the bins the rest of the path can touch are kept ([bin_lo, bin_lo+n_bins),
+// memory.  The four rows of an iteration overlap (hop 128, length 512) and read 896 consecutive
+// samples, of which the next iteration keeps 384: the window's samples are staged through a
+// shared-memory ring of three 512-sample blocks, one TMA bulk copy (cp.async.bulk, 4 KB) per
+// iteration issued two blocks ahead and tracked by an mbarrier, so every sample crosses
+// L2 -> shared memory once and no thread holds prefetched samples in registers.  Only the bins the rest of the path can touch are kept ([bin_lo, bin_lo+n_bins),
 // 42 of 512 at halfbandwidth 10): their amplitudes sqrt(ps) are written once to HBM for
 // the coarse-search kernel (powersum() takes the sqrt of every ps it reads,
 // FDR_impl.cc:199-205; IEEE sqrtf is deterministic, so hoisting it is exact), and their
@@ -22,6 +26,32 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kGroups = 4;
+constexpr int kBlk = kGroups * UW_HOP;   // samples an iteration advances by (512) = one ring block
+constexpr int kRingBlocks = 3;
+
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(smem_addr(bar)),
+                 "r"(parity)
+                 : "memory");
+}
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -59,6 +89,7 @@ __device__ __forceinline__ void fft8(float2 *v)
 #define PADX(i) ((i) + ((i) >> 3))
 
 struct __align__(16) SpecSmem {
+    float2 xring[kRingBlocks][kBlk];               // the window's samples, block b in slot b % 3
     float2 buf[kGroups][UW_FFT_N + UW_FFT_N / 8];  // inter-pass exchange, one FFT per group, padded (PADX)
     float2 tw1[8][8];                // pass-1 twiddles exp(-2 pi i 8 r k / 512), [r][k]
     float2 tw2[8][64];               // pass-2 twiddles exp(-2 pi i r j / 512), [r][j]
@@ -69,6 +100,7 @@ struct __align__(16) SpecSmem {
     int npk;
     UwPeak peaks[256];
     UwPeak sorted[256];
+    uint64_t bar[kRingBlocks];       // one mbarrier per ring slot
 };
 
 // 4 CTAs/SM (64 registers) measured 4.6 % faster than 3 (80 registers) and 20 % faster than 2;
@@ -107,28 +139,48 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     __syncthreads();
 
     const int n_iter = (d.n_rows + kGroups - 1) / kGroups;
-    // samples of the next iteration are fetched while the current FFT runs
-    float2 nx[8];
-    {
-        const bool l0 = g < d.n_rows;
-        const float2 *src = xw + (long long)g * UW_HOP + j;
+    // Sample staging.  Iteration `it` reads samples [512 it, 512 it + 896): ring blocks it and it + 1; block it + 2
+    // is fetched while it runs.  Windows that start on a 16-byte boundary use one bulk copy per block (thread 0
+    // arms the slot's mbarrier with the byte count and issues it); others (odd sample strides such as the 9 s
+    // sliding window) copy with plain loads, ordered by the loop's own barriers.
+    const int nblk = (d.fl + kBlk - 1) / kBlk;
+    const bool bulk = (reinterpret_cast<unsigned long long>(xw) & 15ull) == 0ull;
+    auto fetch_block = [&](int b) {
+        if (b >= nblk) return;
+        const int cnt = min(kBlk, d.fl - b * kBlk);          // the last block is short (45000 = 87 * 512 + 456)
+        float2 *dst = sm.xring[b % kRingBlocks];
+        if (bulk) {
+            if (tid == 0) {
+                mbar_expect_tx(&sm.bar[b % kRingBlocks], (unsigned)cnt * 8u);
+                bulk_g2s(dst, xw + (long long)b * kBlk, (unsigned)cnt * 8u, &sm.bar[b % kRingBlocks]);
+            }
+        } else {
+            for (int t = tid; t < cnt; t += kThreads) dst[t] = __ldg(xw + (long long)b * kBlk + t);
+        }
+    };
+    if (tid == 0) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) nx[r] = l0 ? __ldg(src + 64 * r) : make_float2(0.f, 0.f);
+        for (int q = 0; q < kRingBlocks; q++) mbar_init(&sm.bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    fetch_block(0);
+    fetch_block(1);
+    if (bulk) mbar_wait(&sm.bar[0], 0);
+    __syncthreads();
     for (int it = 0; it < n_iter; it++) {
         const int row = it * kGroups + g;
         const bool live = row < d.n_rows;
         float2 v[8];
+        // block it + 1 has landed (use k of a slot completes phase k of its mbarrier)
+        if (bulk && it + 1 < nblk) mbar_wait(&sm.bar[(it + 1) % kRingBlocks], (unsigned)((it + 1) / kRingBlocks) & 1u);
         if (live) {
 #pragma unroll
             for (int r = 0; r < 8; r++) {
+                const int o = UW_HOP * g + j + 64 * r;       // offset from sample 512 it, < 896
+                const float2 xv = sm.xring[(it + (o >> 9)) % kRingBlocks][o & (kBlk - 1)];
                 // FDR_impl.cc:230-231: the fp32 sample times the fp32 window, rounded once
-                v[r] = make_float2(__fmul_rn(nx[r].x, wj[r]), __fmul_rn(nx[r].y, wj[r]));
-            }
-            if (row + kGroups < d.n_rows) {
-                const float2 *src = xw + (long long)(row + kGroups) * UW_HOP + j;
-#pragma unroll
-                for (int r = 0; r < 8; r++) nx[r] = __ldg(src + 64 * r);
+                v[r] = make_float2(__fmul_rn(xv.x, wj[r]), __fmul_rn(xv.y, wj[r]));
             }
             // pass 0 (Ns = 1): no twiddles; out[8j + r] = X[r]
             fft8(v);
@@ -136,6 +188,8 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             for (int r = 0; r < 8; r++) sm.buf[g][PADX(8 * j + r)] = v[r];
         }
         __syncthreads();
+        // every thread has read its samples of this iteration: the slot of block it - 1 is free for block it + 2
+        fetch_block(it + 2);
         if (live) {
             // pass 1 (Ns = 8)
             const int k = j & 7;
@@ -326,7 +380,11 @@ void uw_launch_spectrogram(const UwDims &d, const float2 *x, long long win_strid
                            const float *window, const float2 *twiddle, float *amp, float *ps_dbg,
                            float *psavg, UwPeak *peaks, int *npk, cudaStream_t s)
 {
-    static_assert(sizeof(SpecSmem) <= 48 * 1024, "spectrogram shared memory must fit the default limit");
+    static bool attr_set = false;   // above the 48 KB default: opt in once (the attribute belongs to the function)
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_spectrogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
+        attr_set = true;
+    }
     k_spectrogram<<<nwin, kThreads, sizeof(SpecSmem), s>>>(d, x, win_stride, nwin, window, twiddle, amp, ps_dbg,
                                                            psavg, peaks, npk);
 }
