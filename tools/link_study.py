@@ -28,6 +28,11 @@ BYTES = FL * 8 * NWIN
 
 
 def main():
+    # stdout carries the JSON only: libraries (NCCL's version line) write to fd 1, which is pointed at stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
