@@ -3,7 +3,7 @@
 # Usage (on the GPU box, from the repo root): bash tools/final_profile.sh r2
 tag=${1:-r2}
 o=gpurun_out
-quick="--no-cpu-baseline --no-verify --skip overlap50,array64,receiver"
+quick="--no-cpu-baseline --no-verify --skip overlap50,sliding9,array64,receiver"
 timeout 900 python bench.py > $o/${tag}_bench_1gpu.json 2> $o/${tag}_bench_1gpu.err
 timeout 600 python bench.py --impl reference > $o/${tag}_bench_1gpu_reference_arm.json 2> $o/${tag}_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ --csv --log-file $o/${tag}_launches.csv \
