@@ -62,27 +62,39 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 // multiply by -i
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
-// 8-point forward DFT, natural order in and out
+// 8-point forward DFT, natural order in and out.  The complex additions are packed (FADD2: the same two fp32
+// additions as the scalar pair, one issue slot); multiplications by -i and by exp(-i pi/4) work on the halves.
+__device__ __forceinline__ uw_f2 pk2(float2 a) { return uw_pk(a.x, a.y); }
+__device__ __forceinline__ float2 up2(uw_f2 a) { return make_float2(uw_lo(a), uw_hi(a)); }
 __device__ __forceinline__ void fft8(float2 *v)
 {
     const float h = 0.70710678118654752440f;
-    float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
-    float2 a1 = cadd(v[1], v[5]), t5 = csub(v[1], v[5]);
-    float2 a2 = cadd(v[2], v[6]), t6 = csub(v[2], v[6]);
-    float2 a3 = cadd(v[3], v[7]), t7 = csub(v[3], v[7]);
-    float2 a5 = make_float2((t5.x + t5.y) * h, (t5.y - t5.x) * h);   // * exp(-i pi/4)
-    float2 a6 = mul_mi(t6);                                           // * exp(-i pi/2)
-    float2 a7 = make_float2((t7.y - t7.x) * h, -(t7.x + t7.y) * h);  // * exp(-3i pi/4)
-    float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_mi(csub(a1, a3));
-    float2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_mi(csub(a5, a7));
-    v[0] = cadd(b0, b1);
-    v[4] = csub(b0, b1);
-    v[2] = cadd(b2, b3);
-    v[6] = csub(b2, b3);
-    v[1] = cadd(b4, b5);
-    v[5] = csub(b4, b5);
-    v[3] = cadd(b6, b7);
-    v[7] = csub(b6, b7);
+    const uw_f2 v0 = pk2(v[0]), v1 = pk2(v[1]), v2 = pk2(v[2]), v3 = pk2(v[3]), v4 = pk2(v[4]), v5 = pk2(v[5]), v6 = pk2(v[6]),
+                v7 = pk2(v[7]);
+    const uw_f2 a0 = uw_add2(v0, v4), a4 = uw_sub2(v0, v4);
+    const uw_f2 a1 = uw_add2(v1, v5);
+    const float2 t5 = up2(uw_sub2(v1, v5));
+    const uw_f2 a2 = uw_add2(v2, v6);
+    const float2 t6 = up2(uw_sub2(v2, v6));
+    const uw_f2 a3 = uw_add2(v3, v7);
+    const float2 t7 = up2(uw_sub2(v3, v7));
+    const uw_f2 a5 = uw_pk((t5.x + t5.y) * h, (t5.y - t5.x) * h);   // * exp(-i pi/4)
+    const uw_f2 a6 = uw_pk(t6.y, -t6.x);                             // * exp(-i pi/2)
+    const uw_f2 a7 = uw_pk((t7.y - t7.x) * h, -(t7.x + t7.y) * h);  // * exp(-3i pi/4)
+    const uw_f2 b0 = uw_add2(a0, a2), b2 = uw_sub2(a0, a2), b1 = uw_add2(a1, a3);
+    const float2 d13 = up2(uw_sub2(a1, a3));
+    const uw_f2 b3 = uw_pk(d13.y, -d13.x);                           // -i (a1 - a3)
+    const uw_f2 b4 = uw_add2(a4, a6), b6 = uw_sub2(a4, a6), b5 = uw_add2(a5, a7);
+    const float2 d57 = up2(uw_sub2(a5, a7));
+    const uw_f2 b7 = uw_pk(d57.y, -d57.x);                           // -i (a5 - a7)
+    v[0] = up2(uw_add2(b0, b1));
+    v[4] = up2(uw_sub2(b0, b1));
+    v[2] = up2(uw_add2(b2, b3));
+    v[6] = up2(uw_sub2(b2, b3));
+    v[1] = up2(uw_add2(b4, b5));
+    v[5] = up2(uw_sub2(b4, b5));
+    v[3] = up2(uw_add2(b6, b7));
+    v[7] = up2(uw_sub2(b6, b7));
 }
 
 // one pad slot every 8 entries: the stride-8 stores of the Stockham passes become stride 9
@@ -105,6 +117,8 @@ struct __align__(16) SpecSmem {
 
 // 4 CTAs/SM (64 registers) measured 4.6 % faster than 3 (80 registers) and 20 % faster than 2;
 // 64-thread named barriers for the group-local exchanges measured 2 % slower than __syncthreads
+// FULL: the row count is a multiple of the four groups (348 = 4 x 87 for the reference's frame length), no row tests
+template <bool FULL>
 __global__ void __launch_bounds__(kThreads, 4)
 k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int nwin,
               const float *__restrict__ window, const float2 *__restrict__ twiddle,
@@ -145,14 +159,14 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     // sliding window) copy with plain loads, ordered by the loop's own barriers.
     const int nblk = (d.fl + kBlk - 1) / kBlk;
     const bool bulk = (reinterpret_cast<unsigned long long>(xw) & 15ull) == 0ull;
-    auto fetch_block = [&](int b) {
+    auto fetch_block = [&](int b, int slot) {
         if (b >= nblk) return;
         const int cnt = min(kBlk, d.fl - b * kBlk);          // the last block is short (45000 = 87 * 512 + 456)
-        float2 *dst = sm.xring[b % kRingBlocks];
+        float2 *dst = sm.xring[slot];
         if (bulk) {
             if (tid == 0) {
-                mbar_expect_tx(&sm.bar[b % kRingBlocks], (unsigned)cnt * 8u);
-                bulk_g2s(dst, xw + (long long)b * kBlk, (unsigned)cnt * 8u, &sm.bar[b % kRingBlocks]);
+                mbar_expect_tx(&sm.bar[slot], (unsigned)cnt * 8u);
+                bulk_g2s(dst, xw + (long long)b * kBlk, (unsigned)cnt * 8u, &sm.bar[slot]);
             }
         } else {
             for (int t = tid; t < cnt; t += kThreads) dst[t] = __ldg(xw + (long long)b * kBlk + t);
@@ -164,47 +178,65 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    fetch_block(0);
-    fetch_block(1);
+    fetch_block(0, 0);
+    fetch_block(1, 1);
     if (bulk) mbar_wait(&sm.bar[0], 0);
     __syncthreads();
+    // Everything the loop indexes with is fixed per thread: the exchange positions of the three passes (the padded
+    // index PADX(i) = i + i/8 of 8j+r, j+64r and j0+8r is a base plus 9r, 72r and 9r), the twiddle columns, and which
+    // of the eight samples of a row come from the second of the iteration's two ring blocks (offset 128 g + j + 64 r
+    // >= 512, i.e. r >= 8 - 2 g: the same for a whole warp).
+    float2 *const ex0 = &sm.buf[g][9 * j];
+    const float2 *const ex1 = &sm.buf[g][j + (j >> 3)];
+    float2 *const ex2 = &sm.buf[g][(j >> 3) * 72 + (j & 7)];
+    const float2 *const tw1c = &sm.tw1[0][j & 7];
+    const float2 *const tw2c = &sm.tw2[0][j];
+    const int r_hi = 8 - 2 * g;
+    const int base = UW_HOP * g + j;
+    int s0 = 0;                              // ring slot of block `it`
+    unsigned waited = 1u;                    // bit s: parity of the next wait on slot s (slot 0 was waited for once)
+    float *amp_row = amp + ((long long)win * d.n_rows + g) * d.nbp;
+    float *dbg_row = ps_dbg ? ps_dbg + ((long long)win * d.n_rows + g) * d.nbp : nullptr;
+    const long long row_step = (long long)kGroups * d.nbp;
     for (int it = 0; it < n_iter; it++) {
         const int row = it * kGroups + g;
-        const bool live = row < d.n_rows;
+        const bool live = FULL || row < d.n_rows;
+        const int s1 = s0 == kRingBlocks - 1 ? 0 : s0 + 1, s2 = s0 == 0 ? kRingBlocks - 1 : s0 - 1;
         float2 v[8];
         // block it + 1 has landed (use k of a slot completes phase k of its mbarrier)
-        if (bulk && it + 1 < nblk) mbar_wait(&sm.bar[(it + 1) % kRingBlocks], (unsigned)((it + 1) / kRingBlocks) & 1u);
+        if (bulk && it + 1 < nblk) {
+            mbar_wait(&sm.bar[s1], (waited >> s1) & 1u);
+            waited ^= 1u << s1;
+        }
         if (live) {
+            const float2 *lo = &sm.xring[s0][base], *hi = &sm.xring[s1][base] - kBlk;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const int o = UW_HOP * g + j + 64 * r;       // offset from sample 512 it, < 896
-                const float2 xv = sm.xring[(it + (o >> 9)) % kRingBlocks][o & (kBlk - 1)];
+                const float2 xv = (r >= r_hi ? hi : lo)[64 * r];
                 // FDR_impl.cc:230-231: the fp32 sample times the fp32 window, rounded once
                 v[r] = make_float2(__fmul_rn(xv.x, wj[r]), __fmul_rn(xv.y, wj[r]));
             }
             // pass 0 (Ns = 1): no twiddles; out[8j + r] = X[r]
             fft8(v);
 #pragma unroll
-            for (int r = 0; r < 8; r++) sm.buf[g][PADX(8 * j + r)] = v[r];
+            for (int r = 0; r < 8; r++) ex0[r] = v[r];
         }
         __syncthreads();
         // every thread has read its samples of this iteration: the slot of block it - 1 is free for block it + 2
-        fetch_block(it + 2);
+        fetch_block(it + 2, s2);
         if (live) {
             // pass 1 (Ns = 8)
-            const int k = j & 7;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 s = sm.buf[g][PADX(j + 64 * r)];
-                v[r] = (r == 0) ? s : cmul(s, sm.tw1[r][k]);
+                float2 sv = ex1[72 * r];
+                v[r] = (r == 0) ? sv : cmul(sv, tw1c[8 * r]);
             }
             fft8(v);
         }
         __syncthreads();
         if (live) {
-            const int j0 = (j >> 3) * 64 + (j & 7);
 #pragma unroll
-            for (int r = 0; r < 8; r++) sm.buf[g][PADX(j0 + 8 * r)] = v[r];
+            for (int r = 0; r < 8; r++) ex2[9 * r] = v[r];
         }
         __syncthreads();
         if (live && keep) {
@@ -212,8 +244,8 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             // per thread at most (X[j] below DC+, X[j+448] above): those are summed directly
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 s = sm.buf[g][PADX(j + 64 * r)];
-                v[r] = (r == 0) ? s : cmul(s, sm.tw2[r][j]);
+                float2 sv = ex1[72 * r];
+                v[r] = (r == 0) ? sv : cmul(sv, tw2c[64 * r]);
             }
             if (keep == 0x01u) {
                 v[0] = cadd(cadd(cadd(v[0], v[4]), cadd(v[2], v[6])), cadd(cadd(v[1], v[5]), cadd(v[3], v[7])));
@@ -228,8 +260,6 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             } else {
                 fft8(v);
             }
-            float *amp_row = amp + ((long long)win * d.n_rows + row) * d.nbp;
-            float *dbg_row = ps_dbg ? ps_dbg + ((long long)win * d.n_rows + row) * d.nbp : nullptr;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 // narrow bands keep exactly one output per thread (r = 0 or r = 7): skip the other tests
@@ -246,14 +276,23 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
                 }
             }
         }
+        amp_row += row_step;
+        if (dbg_row) dbg_row += row_step;
+        s0 = s1;
         __syncthreads();
         // :257-263 column sums in row order
         {
-            const int rows_here = min(kGroups, d.n_rows - it * kGroups);
-            if (tid < nb)
-                for (int q = 0; q < rows_here; q++) acc0 = __fadd_rn(acc0, sm.psrow[q][tid]);
-            if (tid + kThreads < nb)
-                for (int q = 0; q < rows_here; q++) acc1 = __fadd_rn(acc1, sm.psrow[q][tid + kThreads]);
+            const int rows_here = FULL ? kGroups : min(kGroups, d.n_rows - it * kGroups);
+            if (tid < nb) {
+#pragma unroll
+                for (int q = 0; q < kGroups; q++)
+                    if (q < rows_here) acc0 = __fadd_rn(acc0, sm.psrow[q][tid]);
+            }
+            if (tid + kThreads < nb) {
+#pragma unroll
+                for (int q = 0; q < kGroups; q++)
+                    if (q < rows_here) acc1 = __fadd_rn(acc1, sm.psrow[q][tid + kThreads]);
+            }
         }
         // psrow is rewritten only after the next iteration's three barriers
     }
@@ -265,11 +304,11 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     }
 
     // :265-275 smoothing over +-3 bins, accumulated in the order j = -3..3 from 0.0f
-    const int base = d.m - d.hpbm - d.bin_lo;  // kept-bin index of shifted bin m-hpbm
+    const int band0 = d.m - d.hpbm - d.bin_lo;  // kept-bin index of shifted bin m-hpbm
     for (int i = tid; i < d.finpb; i += kThreads) {
         float a = 0.0f;
 #pragma unroll
-        for (int q = -3; q <= 3; q++) a = __fadd_rn(a, sm.psavg[base + i + q]);
+        for (int q = -3; q <= 3; q++) a = __fadd_rn(a, sm.psavg[band0 + i + q]);
         sm.smspec[i] = a;
     }
     __syncthreads();
@@ -382,11 +421,16 @@ void uw_launch_spectrogram(const UwDims &d, const float2 *x, long long win_strid
 {
     static bool attr_set = false;   // above the 48 KB default: opt in once (the attribute belongs to the function)
     if (!attr_set) {
-        cudaFuncSetAttribute(k_spectrogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
+        cudaFuncSetAttribute(k_spectrogram<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
+        cudaFuncSetAttribute(k_spectrogram<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem));
         attr_set = true;
     }
-    k_spectrogram<<<nwin, kThreads, sizeof(SpecSmem), s>>>(d, x, win_stride, nwin, window, twiddle, amp, ps_dbg,
-                                                           psavg, peaks, npk);
+    if (d.n_rows % kGroups == 0)
+        k_spectrogram<true><<<nwin, kThreads, sizeof(SpecSmem), s>>>(d, x, win_stride, nwin, window, twiddle, amp, ps_dbg, psavg,
+                                                                     peaks, npk);
+    else
+        k_spectrogram<false><<<nwin, kThreads, sizeof(SpecSmem), s>>>(d, x, win_stride, nwin, window, twiddle, amp, ps_dbg, psavg,
+                                                                      peaks, npk);
 }
 
 void uw_launch_worklist(const int *npk, int nwin, int cap, int *base, UwItem *items, int *counters,
