@@ -48,6 +48,8 @@ struct Knobs {
     int dev_chunks = 1;         // UWSPR_B200_DEV_CHUNKS
     int fine_ctas_per_sm = 0;   // UWSPR_B200_FINE_CTAS_PER_SM: fewer resident CTAs than fit (occupancy experiments)
     int fine_slice = 16384;     // UWSPR_B200_FINE_SLICE: candidates per pass of the fine path's stage sequence
+    int fine_slice_side = 16384; // UWSPR_B200_FINE_SLICE_SIDE: the same for the second and third compute stream (host-fed
+                                // 100 000-window stream: 4096 / 8192 / 16384 -> 247 / 283 / 294 k windows/s)
 };
 
 Knobs read_knobs()
@@ -66,12 +68,13 @@ Knobs read_knobs()
     k.dev_chunks = std::max(1, geti("UWSPR_B200_DEV_CHUNKS", 1));
     k.fine_ctas_per_sm = std::max(0, geti("UWSPR_B200_FINE_CTAS_PER_SM", 0));
     k.fine_slice = std::max(1, geti("UWSPR_B200_FINE_SLICE", k.fine_slice));
+    k.fine_slice_side = std::max(1, geti("UWSPR_B200_FINE_SLICE_SIDE", k.fine_slice_side));
     return k;
 }
 
 struct Buffers {
     // per chunk
-    float2 *x_stage[2] = { nullptr, nullptr };  // host-fed samples, double buffered
+    float2 *x_stage[3] = { nullptr, nullptr, nullptr };  // host-fed samples, three buffer sets
     size_t x_stage_elems = 0;
     float *amp = nullptr;
     float *ps_dbg = nullptr;
@@ -113,12 +116,12 @@ struct uwspr_b200_ctx {
     cudaStream_t compute = nullptr, compute2 = nullptr, compute3 = nullptr, copy = nullptr, d2h = nullptr;
     int *h_ends = nullptr;  // pinned: end of every chunk's items (host-fed calls stream results back per chunk)
     bool own_compute = true;
-    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_free[2] = { nullptr, nullptr }, ev_wl[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_h2d[3] = { nullptr, nullptr, nullptr }, ev_free[3] = { nullptr, nullptr, nullptr }, ev_wl[3] = { nullptr, nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int last_cw = 0;
     std::vector<UwChunk> last_chunks;  // schedule of the last call
     Knobs knobs;
-    bool last_host = false;
+    int last_sets = 1;   // buffer sets the last call rotated through
     std::vector<cudaEvent_t> ev;  // 5 per chunk: start, after spec, after coarse, after fine
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t ev_cp0 = nullptr, ev_cp1 = nullptr, ev_kend = nullptr;  // UWSPR_B200_TRACE
@@ -274,12 +277,12 @@ int ensure_stage(uwspr_b200_ctx *ctx, size_t elems)
 {
     Buffers &b = ctx->b;
     if (elems <= b.x_stage_elems) return UWSPR_B200_OK;
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < 3; q++) {
         if (b.x_stage[q]) cudaFree(b.x_stage[q]);
         b.x_stage[q] = nullptr;
     }
     b.x_stage_elems = 0;
-    for (int q = 0; q < 2; q++) CU(cudaMalloc(&b.x_stage[q], elems * sizeof(float2)));
+    for (int q = 0; q < 3; q++) CU(cudaMalloc(&b.x_stage[q], elems * sizeof(float2)));
     b.x_stage_elems = elems;
     return UWSPR_B200_OK;
 }
@@ -321,11 +324,18 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
     // previous chunk's fine kernel
     const Knobs &kn = ctx->knobs;
     const bool two = host || kn.dev_chunks > 1;
+    // Host input rotates through three buffer sets and three compute streams: with two, the copy of chunk c+2 waited
+    // for the kernels of chunk c, which share the GPU with those of chunk c+1 and take longer than a copy when copy
+    // and compute are balanced (a 100 000-window overlapped stream: 15.2 ms per 4 096-window chunk against 13.3 ms
+    // per copy, trace in profiles/README.md).
+    const int nsets = host ? 3 : (two ? 2 : 1);
     // host-fed chunk: small enough that the first kernels start early and little is left after the last byte, large
     // enough that the fine path's launches are well filled (measured on a 100 000-window overlapped stream: 1024 /
     // 2048 / 4096 windows per chunk -> 235 / 248 / 251 k windows/s; a 10 000-window call does not care)
     const int host_chunk = kn.host_chunk > 0 ? kn.host_chunk : std::min(4096, std::max(1024, nwin / 16));
-    const int cw = host ? std::max(1, std::min(host_chunk, ctx->chunk_windows / 2))
+    // a call that fits the chunk buffers is cut in three, so that every window's intermediate buffers survive the call
+    const int set_cap = nwin <= ctx->chunk_windows ? std::max(ctx->chunk_windows / 3, (nwin + 2) / 3) : ctx->chunk_windows / 3;
+    const int cw = host ? std::max(1, std::min(host_chunk, set_cap))
                         : (two ? std::max(1, std::min(ctx->chunk_windows / 2, (nwin + kn.dev_chunks - 1) / kn.dev_chunks))
                                : ctx->chunk_windows);
     // Chunk schedule.  With host input the kernels of a chunk cannot start before its last byte
@@ -339,9 +349,9 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
         const int piece = kn.tail_piece > 0 ? kn.tail_piece : std::max(1, cw / 4);
         if (!host || kn.no_tail_split) tail_groups = 0;
         const int ngroups = (nwin + cw - 1) / cw;
-        int w = 0, cset = 2, rr = 0;
+        int w = 0, cset = nsets, rr = 0;
         for (int group = 0; group < ngroups; group++) {
-            const int gw = std::min(cw, nwin - w), set = two ? (group & 1) : 0;
+            const int gw = std::min(cw, nwin - w), set = group % nsets;
             const bool cut = group > 0 && group >= ngroups - tail_groups && gw > piece;
             if (!cut) {
                 chunks.push_back(UwChunk{ w, gw, set, 0, set, group, set, 0 });
@@ -419,7 +429,7 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
         if (host) {
             // copy stream: wait until the kernels of the chunk two groups back released this buffer
             // set, then copy
-            if (first_of_group && ch.group >= 2) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
+            if (first_of_group && ch.group >= nsets) CU(cudaStreamWaitEvent(ctx->copy, ctx->ev_free[s], 0));
             if (ctx->knobs.trace && c == 0) CU(cudaEventRecord(ctx->ev_cp0, ctx->copy));
             const size_t span = (size_t)(nw - 1) * (size_t)win_stride + (size_t)d.fl;
             CU(cudaMemcpyAsync(b.x_stage[s] + ch.xoff, samples + 2 * (size_t)w0 * (size_t)win_stride, span * sizeof(float2),
@@ -481,7 +491,7 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
         }
     }
     ctx->last_cw = cw;
-    ctx->last_host = two;
+    ctx->last_sets = nsets;
     if (ctx->knobs.trace) CU(cudaEventRecord(ctx->ev_kend, cs));
     int done = 0;  // results [0, done) are already on their way to the caller
     auto fetch = [&](int lo, int hi, cudaStream_t q) -> cudaError_t {
@@ -671,7 +681,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     // the first stream carries the large chunks of device-resident input; the other two only see host-fed chunks
     // (<= 1024 windows, pieces of a quarter of that)
     for (int q = 0; q < 3; q++) {
-        ctx->fine_slice[q] = std::max(1, std::min(ctx->max_candidates, q == 0 ? ctx->knobs.fine_slice : std::min(ctx->knobs.fine_slice, 4096)));
+        ctx->fine_slice[q] = std::max(1, std::min(ctx->max_candidates, q == 0 ? ctx->knobs.fine_slice : std::min(ctx->knobs.fine_slice, ctx->knobs.fine_slice_side)));
         CUC(cudaMalloc(&b.fine_state[q], (size_t)ctx->fine_slice[q] * uw_fine_state_bytes()));
         CUC(cudaMalloc(&b.fine_pbuf[q], (size_t)ctx->fine_slice[q] * uw_fine_pbuf_bytes()));
         CUC(cudaMalloc(&b.fine_pe[q], (size_t)ctx->fine_slice[q] * uw_fine_pe_bytes()));
@@ -703,10 +713,10 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaHostAlloc(&ctx->h_ends, sizeof(int) * (kMaxChunks + 4), cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < 3; q++) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_h2d[q], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&ctx->ev_free[q], cudaEventDisableTiming));
-        CUC(cudaEventCreateWithFlags(&ctx->ev_wl[q], cudaEventDisableTiming));
+        if (q < 2) CUC(cudaEventCreateWithFlags(&ctx->ev_wl[q], cudaEventDisableTiming));
     }
     CUC(cudaEventCreate(&ctx->ev_begin));
     CUC(cudaEventCreate(&ctx->ev_cp0));
@@ -741,16 +751,16 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     if (ctx->pending.valid()) ctx->pending.wait();
     cudaSetDevice(ctx->device);
     Buffers &b = ctx->b;
-    void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
+    void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.x_stage[2], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
                      b.cands, b.refined, b.jig, b.soft, b.counters, b.fine_tickets, b.fine_state[0], b.fine_state[1], b.fine_state[2], b.fine_pbuf[0], b.fine_pbuf[1],
                      b.fine_pbuf[2], b.fine_pe[0], b.fine_pe[1], b.fine_pe[2], b.fine_tables[0], b.fine_tables[1], b.fine_tables[2], b.window, b.twiddle, b.off4, b.hyp_unique };
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < 3; q++) {
         if (ctx->ev_h2d[q]) cudaEventDestroy(ctx->ev_h2d[q]);
         if (ctx->ev_free[q]) cudaEventDestroy(ctx->ev_free[q]);
-        if (ctx->ev_wl[q]) cudaEventDestroy(ctx->ev_wl[q]);
+        if (q < 2 && ctx->ev_wl[q]) cudaEventDestroy(ctx->ev_wl[q]);
     }
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_cp0) cudaEventDestroy(ctx->ev_cp0);
@@ -899,13 +909,13 @@ int uwspr_b200_debug_spectrogram(uwspr_b200_ctx *ctx, int win, float *ps, float 
 {
     if (!ctx) return UWSPR_B200_E_PARAM;
     if (!ctx->debug_ps || !ctx->b.ps_dbg) return fail(ctx, UWSPR_B200_E_STATE, "enable uwspr_b200_set_debug first");
-    // the chunk buffers keep the last chunk (device input) or the last two (host input, two sets)
+    // the chunk buffers keep the last chunk (device input) or the last chunks of every buffer set (host input)
     const int cw = ctx->last_cw > 0 ? ctx->last_cw : 1;
     const std::vector<UwChunk> &chunks = ctx->last_chunks;
     const UwChunk *ch = nullptr;
     for (const UwChunk &q : chunks)
         if (win >= q.w0 && win < q.w0 + q.nw) ch = &q;
-    if (win < 0 || win >= ctx->last_nwin || !ch || ch->group < chunks.back().group - (ctx->last_host ? 1 : 0))
+    if (win < 0 || win >= ctx->last_nwin || !ch || ch->group < chunks.back().group - (ctx->last_sets - 1))
         return fail(ctx, UWSPR_B200_E_PARAM, "window is not in the chunks still held on the device");
     const size_t slot = (size_t)ch->set * cw + (size_t)ch->slot + (size_t)(win - ch->w0);
     CU(cudaSetDevice(ctx->device));
