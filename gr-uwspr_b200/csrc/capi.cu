@@ -94,6 +94,7 @@ struct Buffers {
     void *fine_state[3] = { nullptr, nullptr, nullptr };
     void *fine_pbuf[3] = { nullptr, nullptr, nullptr };
     void *fine_pe[3] = { nullptr, nullptr, nullptr };
+    void *fine_pbest[3] = { nullptr, nullptr, nullptr };
     void *fine_tables[3] = { nullptr, nullptr, nullptr };
     int *counters = nullptr;  // [0] running total, [1] overflow; set s at 4+4s: ticket coarse, ticket fine, end of chunk
     // tables
@@ -476,7 +477,7 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
             for (long long s0 = 0; s0 < most; s0 += slice)
                 ctx->launches += uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 1, set + 2, ctx->max_candidates, b.cands,
                                                 jig_first, jig_count, b.refined, b.jig, b.soft, (int)s0, slice,
-                                                b.fine_state[ch.strm], b.fine_pbuf[ch.strm], b.fine_pe[ch.strm], b.fine_tables[ch.strm], b.fine_tickets + 16 * ch.strm, ctx->grid_points,
+                                                b.fine_state[ch.strm], b.fine_pbuf[ch.strm], b.fine_pe[ch.strm], b.fine_pbest[ch.strm], b.fine_tables[ch.strm], b.fine_tickets + 16 * ch.strm, ctx->grid_points,
                                                 ctx->grid_lags, st);
         }
         CU(cudaEventRecord(e[3], st));
@@ -685,6 +686,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
         CUC(cudaMalloc(&b.fine_state[q], (size_t)ctx->fine_slice[q] * uw_fine_state_bytes()));
         CUC(cudaMalloc(&b.fine_pbuf[q], (size_t)ctx->fine_slice[q] * uw_fine_pbuf_bytes()));
         CUC(cudaMalloc(&b.fine_pe[q], (size_t)ctx->fine_slice[q] * uw_fine_pe_bytes()));
+        CUC(cudaMalloc(&b.fine_pbest[q], (size_t)ctx->fine_slice[q] * uw_fine_pbest_bytes()));
         CUC(cudaMalloc(&b.fine_tables[q], (size_t)ctx->fine_slice[q] * uw_fine_tables_bytes()));
     }
     // tables
@@ -753,7 +755,7 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     Buffers &b = ctx->b;
     void *ptrs[] = { b.x_stage[0], b.x_stage[1], b.x_stage[2], b.amp, b.ps_dbg, b.psavg, b.peaks, b.npk, b.base, b.items,
                      b.cands, b.refined, b.jig, b.soft, b.counters, b.fine_tickets, b.fine_state[0], b.fine_state[1], b.fine_state[2], b.fine_pbuf[0], b.fine_pbuf[1],
-                     b.fine_pbuf[2], b.fine_pe[0], b.fine_pe[1], b.fine_pe[2], b.fine_tables[0], b.fine_tables[1], b.fine_tables[2], b.window, b.twiddle, b.off4, b.hyp_unique };
+                     b.fine_pbuf[2], b.fine_pe[0], b.fine_pe[1], b.fine_pe[2], b.fine_pbest[0], b.fine_pbest[1], b.fine_pbest[2], b.fine_tables[0], b.fine_tables[1], b.fine_tables[2], b.window, b.twiddle, b.off4, b.hyp_unique };
     for (void *q : ptrs)
         if (q) cudaFree(q);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
