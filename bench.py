@@ -490,9 +490,10 @@ def run_ours(args):
     info_nbp = 44
     fine_alg_t = evals * FLOP_POINT / (fine_ms * 1e-3) / 1e12
     # executed fp32 lane-operations of the fine path per candidate: the chain evaluates 19 new points with
-    # routine R1 (14 mul/add per tone-sample: 8 for the two correlations, 6 for the table rotation) and 17 jiggles
-    # with R2 (8 per lag + 6 per lag group of <= 5, 4 groups); the packed forms carry two of them per instruction
-    fine_exec = gated * (19 * 14 + (17 * 8 + 4 * 6)) * 162 * 4 * 256 + (ncand - gated) * 11 * 14 * 162 * 4 * 256
+    # routine R1 (14 mul/add per tone-sample: 8 for the two correlations, 6 for the table rotation) and 16 jiggles
+    # with R2 (8 per lag + 6 per lag group of 4, 4 groups; jiggle 0 is the refined point itself and is taken from the
+    # stage that evaluated it); the packed forms carry two of them per instruction
+    fine_exec = gated * (19 * 14 + (16 * 8 + 4 * 6)) * 162 * 4 * 256 + (ncand - gated) * 11 * 14 * 162 * 4 * 256
     fine_exec_t = fine_exec / (fine_ms * 1e-3) / 1e12
     coarse_alg_t = ncand * flop_coarse(PARAMS["maxdrift"]) / (coarse_ms * 1e-3) / 1e12
     spec_bytes = nwin * (360000.0 + 348 * info_nbp * 4)

@@ -45,6 +45,7 @@ struct Knobs {
     bool no_tail_split = false; // UWSPR_B200_NO_TAIL_SPLIT
     bool no_early_d2h = false;  // UWSPR_B200_NO_EARLY_D2H
     bool trace = false;         // UWSPR_B200_TRACE
+    bool no_fine_reuse = false; // UWSPR_B200_NO_FINE_REUSE: stage E evaluates jiggle 0 again instead of taking it from the chain
     int dev_chunks = 1;         // UWSPR_B200_DEV_CHUNKS
     int fine_ctas_per_sm = 0;   // UWSPR_B200_FINE_CTAS_PER_SM: fewer resident CTAs than fit (occupancy experiments)
     int fine_slice = 16384;     // UWSPR_B200_FINE_SLICE: candidates per pass of the fine path's stage sequence
@@ -65,6 +66,7 @@ Knobs read_knobs()
     k.no_tail_split = getenv("UWSPR_B200_NO_TAIL_SPLIT") != nullptr;
     k.no_early_d2h = getenv("UWSPR_B200_NO_EARLY_D2H") != nullptr;
     k.trace = getenv("UWSPR_B200_TRACE") != nullptr;
+    k.no_fine_reuse = getenv("UWSPR_B200_NO_FINE_REUSE") != nullptr;
     k.dev_chunks = std::max(1, geti("UWSPR_B200_DEV_CHUNKS", 1));
     k.fine_ctas_per_sm = std::max(0, geti("UWSPR_B200_FINE_CTAS_PER_SM", 0));
     k.fine_slice = std::max(1, geti("UWSPR_B200_FINE_SLICE", k.fine_slice));
@@ -478,7 +480,7 @@ int run_impl(uwspr_b200_ctx *ctx, const float *samples, int space, int64_t win_s
                 ctx->launches += uw_launch_fine(d, xdev, (long long)win_stride, b.items, set + 1, set + 2, ctx->max_candidates, b.cands,
                                                 jig_first, jig_count, b.refined, b.jig, b.soft, (int)s0, slice,
                                                 b.fine_state[ch.strm], b.fine_pbuf[ch.strm], b.fine_pe[ch.strm], b.fine_pbest[ch.strm], b.fine_tables[ch.strm], b.fine_tickets + 16 * ch.strm, ctx->grid_points,
-                                                ctx->grid_lags, st);
+                                                ctx->grid_lags, kn.no_fine_reuse ? 0 : 1, st);
         }
         CU(cudaEventRecord(e[3], st));
         if (host) CU(cudaEventRecord(ctx->ev_free[s], st));

@@ -124,7 +124,7 @@ int uw_launch_fine(const UwDims &d, const float2 *x, long long win_stride, const
                    const int *end, int cap, const uwspr_b200_candidate_t *cands, int jig_first, int jig_count,
                    uwspr_b200_refined_t *refined, uwspr_b200_jiggle_t *jig, uint8_t *soft, int slice0, int slice_n,
                    void *state, void *pbuf, void *pE, void *pbest, void *tables, int *tickets, int grid_points, int grid_lags,
-                   cudaStream_t s);
+                   int reuse, cudaStream_t s);
 size_t uw_fine_state_bytes();   // per candidate of a slice: chain state, stage magnitudes, jiggle magnitudes
 size_t uw_fine_pbuf_bytes();
 size_t uw_fine_pe_bytes();

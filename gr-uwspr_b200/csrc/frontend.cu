@@ -12,8 +12,13 @@
 // with x[n] = 0 outside [0, n_in) (the zero history of a GNU Radio FIR).  It pays off when many
 // channels of audio are already on the device (the 64-hydrophone array of BASELINE.json
 // configs[4]): the 375-sps output feeds uwspr_b200_coarse_fine as a device pointer.
-// No parity oracle exists for GNU Radio's own blocks in this environment; the tests check the
-// formula above against a float64 numpy evaluation.
+// taps may be complex (uwspr_b200_frontend_ctaps): the flowgraph's cascade - real band-pass around fc,
+// translate by fc + low-pass, rational resampler 1/32 - collapses into one complex composite filter
+// (h_bp[k] e^{-i w k}) * h_lp * h_rs applied to the mixed-down input (uwspr_b200/binding.py flowgraph_taps).
+// GNU Radio itself is not available here: oracle/gr_frontend.py restates its blocks one by one in
+// float64 from their published algorithms (gr-filter 3.7: firdes, freq_xlating_fft_filter, rational_resampler)
+// and the GPU test compares this kernel with that chain; tests/test_gpu_parity.py also checks the formula above
+// against a float64 numpy evaluation.
 #include <string>
 
 #include "common.cuh"
@@ -23,6 +28,7 @@ namespace {
 constexpr int kFeOut = 64;      // outputs per CTA
 constexpr int kFeThreads = 256; // 8 warps x 8 outputs
 
+template <bool CTAPS>
 __global__ void __launch_bounds__(kFeThreads)
 k_frontend(const void *__restrict__ audio, int fmt, long long chan_stride, long long n_in,
            const float *__restrict__ taps, int ntaps, int decim, int delay, double cyc_per_sample,
@@ -54,12 +60,17 @@ k_frontend(const void *__restrict__ audio, int fmt, long long chan_stride, long 
     for (int o = 0; o < 8; o++) acc[o] = make_float2(0.0f, 0.0f);
     const float2 *zw = z + (warp * 8) * decim + (ntaps - 1);
     for (int k = lane; k < ntaps; k += 32) {
-        const float h = __ldg(taps + k);
+        const float h = CTAPS ? __ldg(taps + 2 * k) : __ldg(taps + k);
+        const float hi = CTAPS ? __ldg(taps + 2 * k + 1) : 0.0f;
 #pragma unroll
         for (int o = 0; o < 8; o++) {
             const float2 s = zw[o * decim - k];
             acc[o].x = fmaf(h, s.x, acc[o].x);
             acc[o].y = fmaf(h, s.y, acc[o].y);
+            if (CTAPS) {
+                acc[o].x = fmaf(-hi, s.y, acc[o].x);
+                acc[o].y = fmaf(hi, s.x, acc[o].y);
+            }
         }
     }
 #pragma unroll
@@ -97,9 +108,9 @@ int fe_fail(int st, const std::string &msg)
 
 extern "C" const char *uwspr_b200_frontend_error(void) { return g_fe_error.c_str(); }
 
-extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int space_in, int64_t chan_stride, int nchan,
-                                   int64_t n_in, const float *taps, int ntaps, int decim, int delay, double fc,
-                                   double fs_in, float *out, int space_out, int64_t out_stride, int64_t *n_out_p)
+static int frontend_impl(bool ctaps, int device, const void *audio, int fmt, int space_in, int64_t chan_stride, int nchan,
+                         int64_t n_in, const float *taps, int ntaps, int decim, int delay, double fc,
+                         double fs_in, float *out, int space_out, int64_t out_stride, int64_t *n_out_p)
 {
     if (!audio || !taps || !out || nchan < 1 || n_in < 1 || ntaps < 1 || ntaps > 16384 || decim < 1 || decim > 4096 ||
         delay < 0 || !(fs_in > 0.0) || (fmt != 0 && fmt != 1) || chan_stride < n_in)
@@ -126,8 +137,9 @@ extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int s
         FE_CU(cudaMalloc(&d_out_own, out_bytes));
         d_out = reinterpret_cast<float2 *>(d_out_own);
     }
-    FE_CU(cudaMalloc(&d_taps, sizeof(float) * (size_t)ntaps));
-    FE_CU(cudaMemcpy(d_taps, taps, sizeof(float) * (size_t)ntaps, cudaMemcpyHostToDevice));
+    const size_t tap_bytes = sizeof(float) * (size_t)ntaps * (ctaps ? 2 : 1);
+    FE_CU(cudaMalloc(&d_taps, tap_bytes));
+    FE_CU(cudaMemcpy(d_taps, taps, tap_bytes, cudaMemcpyHostToDevice));
     const size_t smem = ((size_t)(kFeOut - 1) * decim + ntaps) * sizeof(float2);
     int optin = 0;
     FE_CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -137,10 +149,15 @@ extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int s
         if (d_out_own) cudaFree(d_out_own);
         return fe_fail(UWSPR_B200_E_PARAM, "ntaps + 63*decim samples do not fit shared memory");
     }
-    FE_CU(cudaFuncSetAttribute(k_frontend, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    FE_CU(cudaFuncSetAttribute(k_frontend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    FE_CU(cudaFuncSetAttribute(k_frontend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     const dim3 grid((unsigned)((n_out + kFeOut - 1) / kFeOut), (unsigned)nchan);
-    k_frontend<<<grid, kFeThreads, smem>>>(d_audio, fmt, (long long)chan_stride, (long long)n_in, d_taps, ntaps, decim,
-                                           delay, fc / fs_in, d_out, (long long)out_stride, (long long)n_out);
+    if (ctaps)
+        k_frontend<true><<<grid, kFeThreads, smem>>>(d_audio, fmt, (long long)chan_stride, (long long)n_in, d_taps, ntaps, decim,
+                                                     delay, fc / fs_in, d_out, (long long)out_stride, (long long)n_out);
+    else
+        k_frontend<false><<<grid, kFeThreads, smem>>>(d_audio, fmt, (long long)chan_stride, (long long)n_in, d_taps, ntaps, decim,
+                                                      delay, fc / fs_in, d_out, (long long)out_stride, (long long)n_out);
     FE_CU(cudaGetLastError());
     if (space_out == UWSPR_B200_HOST)
         // channel by channel: the caller's memory between two channels (out_stride > n_out) is not touched
@@ -152,4 +169,20 @@ extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int s
     if (d_audio_own) cudaFree(d_audio_own);
     if (d_out_own) cudaFree(d_out_own);
     return UWSPR_B200_OK;
+}
+
+extern "C" int uwspr_b200_frontend(int device, const void *audio, int fmt, int space_in, int64_t chan_stride, int nchan,
+                                   int64_t n_in, const float *taps, int ntaps, int decim, int delay, double fc,
+                                   double fs_in, float *out, int space_out, int64_t out_stride, int64_t *n_out_p)
+{
+    return frontend_impl(false, device, audio, fmt, space_in, chan_stride, nchan, n_in, taps, ntaps, decim, delay, fc, fs_in, out,
+                         space_out, out_stride, n_out_p);
+}
+
+extern "C" int uwspr_b200_frontend_ctaps(int device, const void *audio, int fmt, int space_in, int64_t chan_stride, int nchan,
+                                         int64_t n_in, const float *taps_iq, int ntaps, int decim, int delay, double fc,
+                                         double fs_in, float *out, int space_out, int64_t out_stride, int64_t *n_out_p)
+{
+    return frontend_impl(true, device, audio, fmt, space_in, chan_stride, nchan, n_in, taps_iq, ntaps, decim, delay, fc, fs_in, out,
+                         space_out, out_stride, n_out_p);
 }

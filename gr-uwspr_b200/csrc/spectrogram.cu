@@ -97,12 +97,15 @@ __device__ __forceinline__ void fft8(float2 *v)
     v[7] = up2(uw_sub2(b6, b7));
 }
 
-// one pad slot every 8 entries: the stride-8 stores of the Stockham passes become stride 9
-#define PADX(i) ((i) + ((i) >> 3))
+// Exchange layout: entry i of a 512-point exchange lives in slot i ^ sw(i), sw = i[6:4] on bits 0..2 and i[6] on
+// bit 3.  A 64-bit shared access is served half a warp at a time from sixteen 8-byte slots; with this swizzle the
+// sixteen lanes of every half-warp hit sixteen different slots in all three access patterns of the Stockham passes
+// (stores to 8j + r, loads from j + 64r, stores to 64(j/8) + j%8 + 8r).  The padded layout this replaces (one spare
+// slot per 8) served the stores but made every load a two-wavefront access: 18 % of the kernel's shared wavefronts.
 
 struct __align__(16) SpecSmem {
     float2 xring[kRingBlocks][kBlk];               // the window's samples, block b in slot b % 3
-    float2 buf[kGroups][UW_FFT_N + UW_FFT_N / 8];  // inter-pass exchange, one FFT per group, padded (PADX)
+    float2 buf[kGroups][UW_FFT_N];   // inter-pass exchange, one FFT per group, swizzled (see above)
     float2 tw1[8][8];                // pass-1 twiddles exp(-2 pi i 8 r k / 512), [r][k]
     float2 tw2[8][64];               // pass-2 twiddles exp(-2 pi i r j / 512), [r][j]
     float psrow[kGroups][UW_FFT_N];  // powers of the kept bins of the four rows of this iteration
@@ -182,13 +185,21 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
     fetch_block(1, 1);
     if (bulk) mbar_wait(&sm.bar[0], 0);
     __syncthreads();
-    // Everything the loop indexes with is fixed per thread: the exchange positions of the three passes (the padded
-    // index PADX(i) = i + i/8 of 8j+r, j+64r and j0+8r is a base plus 9r, 72r and 9r), the twiddle columns, and which
-    // of the eight samples of a row come from the second of the iteration's two ring blocks (offset 128 g + j + 64 r
-    // >= 512, i.e. r >= 8 - 2 g: the same for a whole warp).
-    float2 *const ex0 = &sm.buf[g][9 * j];
-    const float2 *const ex1 = &sm.buf[g][j + (j >> 3)];
-    float2 *const ex2 = &sm.buf[g][(j >> 3) * 72 + (j & 7)];
+    // Everything the loop indexes with is fixed per thread: the exchange positions of the three passes, the twiddle
+    // columns, and which of the eight samples of a row come from the second of the iteration's two ring blocks
+    // (offset 128 g + j + 64 r >= 512, i.e. r >= 8 - 2 g: the same for a whole warp).
+    // Swizzled slots, r = 0..7 (derivation in the layout comment; sw depends on bits 4..6 of the entry only):
+    //   pass-0 stores, entry 8j + r:            ex0 + (r ^ k7),  k7 = (j/2) % 8
+    //   loads, entry j + 64r:                    (r odd ? ex1o : ex1e) + 64r
+    //   pass-1 stores, entry 64(j/8) + j%8 + 8r: ex2 + ((j%4) ^ (r/2)) + 16(r/2) + (r odd ? ex2s : 0)
+    const int jb = (j >> 3) & 1;
+    const int k7 = (j >> 1) & 7;
+    float2 *const ex0 = &sm.buf[g][16 * (j >> 1) + ((8 * (j & 1)) ^ (jb << 3))];
+    const float2 *const ex1e = &sm.buf[g][(j & 48) + ((j & 15) ^ (j >> 4))];
+    const float2 *const ex1o = &sm.buf[g][(j & 48) + ((j & 15) ^ ((j >> 4) | 12))];
+    float2 *const ex2 = &sm.buf[g][64 * (j >> 3) + 4 * (((j >> 2) & 1) ^ jb) + 8 * jb];
+    const int ex2s = jb ? -8 : 8;
+    const int j3 = j & 3;
     const float2 *const tw1c = &sm.tw1[0][j & 7];
     const float2 *const tw2c = &sm.tw2[0][j];
     const int r_hi = 8 - 2 * g;
@@ -219,7 +230,7 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             // pass 0 (Ns = 1): no twiddles; out[8j + r] = X[r]
             fft8(v);
 #pragma unroll
-            for (int r = 0; r < 8; r++) ex0[r] = v[r];
+            for (int r = 0; r < 8; r++) ex0[r ^ k7] = v[r];
         }
         __syncthreads();
         // every thread has read its samples of this iteration: the slot of block it - 1 is free for block it + 2
@@ -228,7 +239,7 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             // pass 1 (Ns = 8)
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 sv = ex1[72 * r];
+                float2 sv = ((r & 1) ? ex1o : ex1e)[64 * r];
                 v[r] = (r == 0) ? sv : cmul(sv, tw1c[8 * r]);
             }
             fft8(v);
@@ -236,7 +247,7 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
         __syncthreads();
         if (live) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) ex2[9 * r] = v[r];
+            for (int r = 0; r < 8; r++) ex2[(j3 ^ (r >> 1)) + 16 * (r >> 1) + ((r & 1) ? ex2s : 0)] = v[r];
         }
         __syncthreads();
         if (live && keep) {
@@ -244,7 +255,7 @@ k_spectrogram(UwDims d, const float2 *__restrict__ x, long long win_stride, int 
             // per thread at most (X[j] below DC+, X[j+448] above): those are summed directly
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                float2 sv = ex1[72 * r];
+                float2 sv = ((r & 1) ? ex1o : ex1e)[64 * r];
                 v[r] = (r == 0) ? sv : cmul(sv, tw2c[64 * r]);
             }
             if (keep == 0x01u) {

@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "uwspr_b200_last_timing", "uwspr_b200_launch_count",
     "uwspr_b200_receiver_create", "uwspr_b200_receiver_destroy", "uwspr_b200_receiver_push", "uwspr_b200_receiver_pop",
     "uwspr_b200_receiver_windows", "uwspr_b200_hashtab_bytes", "uwspr_b200_unpack", "uwspr_b200_format_message_log",
-    "uwspr_b200_pack_type1", "uwspr_b200_channel_symbols", "uwspr_b200_read_c2", "uwspr_b200_frontend",
+    "uwspr_b200_pack_type1", "uwspr_b200_channel_symbols", "uwspr_b200_read_c2", "uwspr_b200_frontend", "uwspr_b200_frontend_ctaps",
     "uwspr_b200_frontend_error", "uwspr_b200_coarse_fine_submit", "uwspr_b200_poll", "uwspr_b200_wait",
 ]
 
@@ -113,6 +113,8 @@ def load_library():
     L.uwspr_b200_frontend.restype = C.c_int
     L.uwspr_b200_frontend.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, vp, C.c_int, C.c_int,
                                       C.c_int, C.c_double, C.c_double, vp, C.c_int, C.c_int64, vp]
+    L.uwspr_b200_frontend_ctaps.restype = C.c_int
+    L.uwspr_b200_frontend_ctaps.argtypes = L.uwspr_b200_frontend.argtypes
     L.uwspr_b200_frontend_error.restype = C.c_char_p
     L.uwspr_b200_host_alloc.restype = C.c_int
     L.uwspr_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -449,13 +451,83 @@ def lowpass_taps(ntaps=513, cutoff=150.0, fs_in=12000.0):
     return (h / h.sum()).astype(np.float32)
 
 
+def _window(name, ntaps, beta):
+    """gr::filter::firdes::window (firdes.cc, GNU Radio 3.7): Hamming 0.54 - 0.46 cos(2 pi n / (N-1)); Kaiser
+    I0(beta sqrt(1 - (2n/(N-1) - 1)^2)) / I0(beta)"""
+    n = np.arange(ntaps, dtype=np.float64)
+    if name == "hamming":
+        return 0.54 - 0.46 * np.cos(2 * np.pi * n / (ntaps - 1))
+    t = 2 * n / (ntaps - 1) - 1
+    return np.i0(beta * np.sqrt(np.maximum(0.0, 1 - t * t))) / np.i0(beta)
+
+
+def _ntaps(fs, width, window, beta):
+    """firdes::compute_ntaps: attenuation of the window (Hamming 53 dB, Kaiser beta/0.1102 + 8.7) * fs / (22 width),
+    made odd"""
+    att = 53.0 if window == "hamming" else beta / 0.1102 + 8.7
+    n = int(att * fs / (22.0 * width))
+    return n | 1
+
+
+def firdes_low_pass(gain, fs, cutoff, width, window="hamming", beta=6.76):
+    """gnuradio.filter.firdes.low_pass: windowed sinc, unit gain at DC times `gain`"""
+    nt = _ntaps(fs, width, window, beta)
+    m = (nt - 1) // 2
+    n = np.arange(-m, m + 1, dtype=np.float64)
+    w0 = 2 * np.pi * cutoff / fs
+    h = np.where(n == 0, w0 / np.pi, np.sin(n * w0) / np.where(n == 0, 1.0, n * np.pi)) * _window(window, nt, beta)
+    return h * (gain / h.sum())
+
+
+def firdes_band_pass(gain, fs, low, high, width, window="hamming", beta=6.76):
+    """gnuradio.filter.firdes.band_pass: difference of two windowed sincs, unit gain at the band centre"""
+    nt = _ntaps(fs, width, window, beta)
+    m = (nt - 1) // 2
+    n = np.arange(-m, m + 1, dtype=np.float64)
+    w0, w1 = 2 * np.pi * low / fs, 2 * np.pi * high / fs
+    h = np.where(n == 0, (w1 - w0) / np.pi, (np.sin(n * w1) - np.sin(n * w0)) / np.where(n == 0, 1.0, n * np.pi))
+    h = h * _window(window, nt, beta)
+    return h * (gain / (h * np.cos(n * (w0 + w1) * 0.5)).sum())
+
+
+def resampler_taps(interp, decim, fractional_bw=0.4):
+    """gnuradio.filter.rational_resampler.design_filter: Kaiser (beta 7) low-pass at the narrower of the two rates"""
+    rate = float(interp) / float(decim)
+    if rate >= 1.0:
+        width = 0.5 - fractional_bw
+        mid = 0.5 - width / 2
+    else:
+        width = rate * (0.5 - fractional_bw)
+        mid = rate * 0.5 - width / 2
+    return firdes_low_pass(interp, interp, mid, width, "kaiser", 7.0)
+
+
+def flowgraph_taps(fs_in=12000.0, fc=1500.0, half_bandwidth=10.0, width=10.0, decim=32):
+    """Composite complex taps of the reference flowgraph's front-end (examples/WaveFilePlusNoiseDecode.grc): band-pass
+    fc -+ half_bandwidth at centre 0 (:322-383, :834-893), translation by fc with a low-pass at fc + half_bandwidth
+    (:384-420, :894-958), rational resampler 1/decim with its default taps (:1753-1810).  With x'[n] = x[n] e^{-iwn}
+    the cascade is y[m] = sum_j g[j] x'[m decim - j], g = (h_bp[k] e^{-iwk}) * h_lp * h_rs: pass g to frontend() with
+    delay 0."""
+    h1 = firdes_band_pass(1.0, fs_in, fc - half_bandwidth, fc + half_bandwidth, width)
+    h2 = firdes_low_pass(1.0, fs_in, fc + half_bandwidth, width)
+    h3 = resampler_taps(1, decim)
+    w = 2 * np.pi * fc / fs_in
+    g = np.convolve(np.convolve(h1 * np.exp(-1j * w * np.arange(len(h1))), h2), h3)
+    return g.astype(np.complex64)
+
+
 def frontend(audio, taps=None, decim=32, fc=1500.0, fs_in=12000.0, delay=None, device=0, out_device_ptr=None,
              out_stride=None):
     """real audio [nchan, n] or [n] (float32, or int16 PCM) at fs_in -> complex64 at fs_in/decim on the GPU
-    (uwspr_b200_frontend).  `audio` may be a numpy array or a (device pointer, dtype, shape) tuple; the result is a
-    numpy array, or stays on the device when out_device_ptr is given.  delay defaults to the filter's group delay."""
+    (uwspr_b200_frontend, or uwspr_b200_frontend_ctaps when the taps are complex).  `audio` may be a numpy array or a
+    (device pointer, dtype, shape) tuple; the result is a numpy array, or stays on the device when out_device_ptr is
+    given.  delay defaults to the filter's group delay."""
     L = load_library()
-    taps = lowpass_taps(fs_in=fs_in) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
+    ctaps = taps is not None and np.iscomplexobj(taps)
+    if ctaps:
+        taps = np.ascontiguousarray(taps, dtype=np.complex64)
+    else:
+        taps = lowpass_taps(fs_in=fs_in) if taps is None else np.ascontiguousarray(taps, dtype=np.float32)
     delay = (len(taps) - 1) // 2 if delay is None else int(delay)
     if isinstance(audio, tuple):
         ptr, dtype, shape = audio
@@ -475,8 +547,9 @@ def frontend(audio, taps=None, decim=32, fc=1500.0, fs_in=12000.0, delay=None, d
         optr, space_out = _p(out), 0
     else:
         out, optr, space_out = None, C.c_void_p(int(out_device_ptr)), 1
-    st = L.uwspr_b200_frontend(device, ptr, fmt, space_in, n_in, nchan, n_in, _p(taps), len(taps), decim, delay, fc, fs_in,
-                               optr, space_out, stride, C.byref(got))
+    entry = L.uwspr_b200_frontend_ctaps if ctaps else L.uwspr_b200_frontend
+    st = entry(device, ptr, fmt, space_in, n_in, nchan, n_in, _p(taps), len(taps), decim, delay, fc, fs_in,
+               optr, space_out, stride, C.byref(got))
     if st != 0:
         raise UwsprError(st, L.uwspr_b200_frontend_error().decode())
     if out is None:

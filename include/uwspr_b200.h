@@ -242,6 +242,15 @@ UWSPR_B200_API int uwspr_b200_frontend(int device, const void *audio, int fmt, i
                                        const float *taps, int ntaps, int decim, int delay, double fc,
                                        double fs_in, float *out, int space_out, int64_t out_stride,
                                        int64_t *n_out);
+/* The same with complex taps (taps_iq: ntaps pairs re, im).  The cascade of the reference's flowgraph
+ * (examples/WaveFilePlusNoiseDecode.grc: freq_xlating_fft_filter_ccc with a real band-pass at centre 0 (:834-893),
+ * freq_xlating_fft_filter_ccc at centre 1500 Hz with a low-pass (:894-958), rational_resampler_xxx 1/32 (:1753-1810))
+ * is one such filter with delay 0: composite = (h_bp[k] e^{-i w k}) * h_lp * h_rs, w = 2 pi fc / fs_in. */
+UWSPR_B200_API int uwspr_b200_frontend_ctaps(int device, const void *audio, int fmt, int space_in,
+                                             int64_t chan_stride, int nchan, int64_t n_in,
+                                             const float *taps_iq, int ntaps, int decim, int delay, double fc,
+                                             double fs_in, float *out, int space_out, int64_t out_stride,
+                                             int64_t *n_out);
 UWSPR_B200_API const char *uwspr_b200_frontend_error(void);
 
 /* The text the reference appends to messagelog.txt for one decoded frame

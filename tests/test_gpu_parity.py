@@ -467,6 +467,48 @@ def test_frontend_audio_to_messages():
         assert mine == [bytes(b) for b in blobs]
 
 
+def test_frontend_equals_the_flowgraph_cascade():
+    """the front-end with the composite complex taps (flowgraph_taps, delay 0) against the block-by-block float64
+    restatement of the flowgraph's GNU Radio blocks (oracle/gr_frontend.py: band-pass at centre 0 -> translation by
+    1500 Hz + low-pass -> rational resampler 1/32; examples/WaveFilePlusNoiseDecode.grc:834-958,1753-1810), on two
+    channels of WSPR audio in noise; then the 375-sps stream decodes to the transmitted texts.
+    Tolerance 5e-6 of the output rms (measured 5..7e-7): float32 products and sums over 6831 taps here, float64 there (GNU Radio's own
+    float32 blocks would not agree with either more closely)."""
+    from oracle import gr_frontend as gf
+    texts = [("VE3EMB", "FN25", 30), ("W1AW", "FN31", 23)]
+    fs_in, n_in = 12000.0, 45000 * 32
+    rng = np.random.default_rng(21)
+    audio = np.zeros((2, n_in))
+    for c, (call, grid, dbm) in enumerate(texts):
+        sym = ub.channel_symbols(ub.pack_type1(call, grid, dbm)).astype(np.float64)
+        f0 = (2.7, -5.2)[c]
+        start = int((0.8 + 0.5 * c) * fs_in)
+        f = 1500.0 + f0 + (np.repeat(sym, 8192) - 1.5) * 375.0 / 256.0
+        audio[c, start:start + 162 * 8192] = 0.1 * np.cos(2 * np.pi * np.cumsum(f) / fs_in)
+        audio[c] += 0.3 * rng.standard_normal(n_in) + 0.4 * np.cos(2 * np.pi * 700.0 * np.arange(n_in) / fs_in)
+    audio32 = audio.astype(np.float32)
+    taps = ub.flowgraph_taps()
+    assert taps.dtype == np.complex64 and len(taps) == 2891 + 2891 + 1051 - 2
+    got = ub.frontend(audio32, taps=taps, delay=0)
+    assert got.shape == (2, 45000)
+    for c in range(2):
+        want = gf.flowgraph_frontend(audio32[c].astype(np.float64))
+        scale = np.sqrt((np.abs(want) ** 2).mean())
+        err = np.abs(got[c] - want).max()
+        print("front-end channel %d: max |gpu - cascade| = %.3g of the output rms" % (c, err / scale))
+        assert err < 5e-6 * scale
+        # the 700 Hz interferer (amplitude 0.4, four times the signal) is gone
+        assert np.abs(want).max() < 0.2
+    ctx = ctx_for(maxdrift=0, max_windows=2)
+    npk, cands, refined, jig, soft = ctx.coarse_fine(got)
+    u = ub.WSPR_unpacker()
+    base = np.concatenate([[0], np.cumsum(npk)])
+    for c, (call, grid, dbm) in enumerate(texts):
+        sl = slice(base[c], base[c + 1])
+        heard = {u.unpack(m)[1] for _, m, _ in ub.decode_candidates(refined[sl], jig[sl], soft[sl])}
+        assert "%s %s %2d" % (call, grid, dbm) in heard
+
+
 @pytest.mark.parametrize("piece,groups,stride", [(3, 2, 45000), (1, 2, 22500), (5, 1, 45000), (2, 2, 3375)])
 def test_host_fed_tail_pieces(piece, groups, stride, monkeypatch):
     """host-fed calls cut their last chunk groups into small pieces on three streams and return results chunk by
@@ -521,6 +563,29 @@ def test_async_submit_equals_the_blocking_call():
     for u, v in zip(want, got):
         assert u.tobytes() == np.asarray(v).tobytes()
     ctx.close()
+
+
+def test_first_jiggle_taken_from_the_chain_equals_its_evaluation(monkeypatch):
+    """stage E answers jiggle 0 (the refined point itself, sync_and_demodulate_impl.cc:461-464 with idt == 0) from the
+    tone magnitudes a stage A-D evaluation of that point left behind; with UWSPR_B200_NO_FINE_REUSE the lag kernel
+    evaluates all 17 lags again: same bytes either way, for all jiggles and for jiggle 0 alone"""
+    xs, _ = td.synth_batch(48, stream=77)
+    ctx = ub.Context(maxdrift=4, max_windows=48)
+    want = ctx.coarse_fine(xs)
+    npk, cands = want[0], want[1]
+    first = ctx.fine(xs, npk, cands, jig_first=0, jig_count=1)
+    ctx.close()
+    monkeypatch.setenv("UWSPR_B200_NO_FINE_REUSE", "1")   # read once, when the context is created
+    ctx = ub.Context(maxdrift=4, max_windows=48)
+    got = ctx.coarse_fine(xs)
+    first_again = ctx.fine(xs, npk, cands, jig_first=0, jig_count=1)
+    ctx.close()
+    assert want[3]["gate"].any()
+    for u, v in zip(want, got):
+        assert u.tobytes() == np.asarray(v).tobytes()
+    for u, v in zip(first, first_again):
+        assert u.tobytes() == np.asarray(v).tobytes()
+    assert first[1][:, 0].tobytes() == want[3][:, 0].tobytes() and first[2][:, 0].tobytes() == want[4][:, 0].tobytes()
 
 
 def test_fine_rejects_inconsistent_candidate_lists():
