@@ -712,7 +712,6 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     CUC(cudaStreamCreateWithFlags(&ctx->compute2, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->compute3, cudaStreamNonBlocking));
-    CUC(cudaEventCreateWithFlags(&ctx->ev_wl[2], cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming));
     CUC(cudaHostAlloc(&ctx->h_ends, sizeof(int) * (kMaxChunks + 4), cudaHostAllocDefault));
     CUC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -720,7 +719,7 @@ int uwspr_b200_create(const uwspr_b200_params_t *params, uwspr_b200_ctx **ctx_ou
     for (int q = 0; q < 3; q++) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_h2d[q], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&ctx->ev_free[q], cudaEventDisableTiming));
-        if (q < 2) CUC(cudaEventCreateWithFlags(&ctx->ev_wl[q], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ctx->ev_wl[q], cudaEventDisableTiming));
     }
     CUC(cudaEventCreate(&ctx->ev_begin));
     CUC(cudaEventCreate(&ctx->ev_cp0));
@@ -764,7 +763,7 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     for (int q = 0; q < 3; q++) {
         if (ctx->ev_h2d[q]) cudaEventDestroy(ctx->ev_h2d[q]);
         if (ctx->ev_free[q]) cudaEventDestroy(ctx->ev_free[q]);
-        if (q < 2 && ctx->ev_wl[q]) cudaEventDestroy(ctx->ev_wl[q]);
+        if (ctx->ev_wl[q]) cudaEventDestroy(ctx->ev_wl[q]);
     }
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_cp0) cudaEventDestroy(ctx->ev_cp0);
@@ -776,7 +775,6 @@ void uwspr_b200_destroy(uwspr_b200_ctx *ctx)
     if (ctx->compute2) cudaStreamDestroy(ctx->compute2);
     if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
     if (ctx->compute3) cudaStreamDestroy(ctx->compute3);
-    if (ctx->ev_wl[2]) cudaEventDestroy(ctx->ev_wl[2]);
     if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
     if (ctx->h_ends) cudaFreeHost(ctx->h_ends);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
